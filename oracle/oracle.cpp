@@ -1,0 +1,76 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY (see gl.h header).  C ABI used by tests/ (ctypes) and by bench.py's
+ * cpu_baseline / --impl reference legs.  Never loaded by the product package. */
+#include <chrono>
+#include <cstdio>
+#include <omp.h>
+#include "commit.h"
+#include "challenger.h"
+
+double orc_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+extern "C" {
+
+int orc_num_threads() { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) { omp_set_num_threads(n); }
+
+void orc_poseidon_permute(u64 *state, int naive) { if (naive) orc_poseidon_naive(state); else orc_poseidon(state); }
+void orc_hash_n(const u64 *in, size_t n, u64 *out, int or_noop) { if (or_noop) orc_hash_or_noop(in, n, out); else orc_hash_no_pad(in, n, out); }
+void orc_compress(const u64 *l, const u64 *r, u64 *out) { orc_two_to_one(l, r, out); }
+
+u64 orc_gl_mul(u64 a, u64 b) { return gl_mul(gl_canon(a), gl_canon(b)); }
+u64 orc_gl_inv(u64 a) { return gl_inv(gl_canon(a)); }
+u64 orc_gl_pow(u64 a, u64 e) { return gl_pow(gl_canon(a), e); }
+u64 orc_root_of_unity(int k) { return gl_root_of_unity(k); }
+
+void orc_fft(u64 *a, int log_n) { size_t n = (size_t)1 << log_n; for (size_t i = 0; i < n; i++) a[i] = gl_canon(a[i]); orc_fft_inplace(a, log_n); }
+void orc_ifft(u64 *a, int log_n) { size_t n = (size_t)1 << log_n; for (size_t i = 0; i < n; i++) a[i] = gl_canon(a[i]); orc_ifft_inplace(a, log_n); }
+void orc_lde(const u64 *coeffs, int log_n, int rate_bits, u64 shift, u64 *out) { orc_coset_lde(coeffs, log_n, rate_bits, shift, out); }
+
+/* ---- PolynomialBatch handle ---- */
+void *orc_batch_from_values_c(const u64 *values, int C, int log_n, int rate_bits, int cap_height) {
+    OrcBatch *b = new OrcBatch();
+    b->num_polys = C; b->degree_log = log_n; b->rate_bits = rate_bits;
+    if (orc_batch_from_values(*b, values, cap_height)) { delete b; return nullptr; }
+    return b;
+}
+void *orc_batch_from_coeffs_c(const u64 *coeffs, int C, int log_n, int rate_bits, int cap_height) {
+    OrcBatch *b = new OrcBatch();
+    b->num_polys = C; b->degree_log = log_n; b->rate_bits = rate_bits;
+    size_t n = (size_t)1 << log_n;
+    b->coeffs.resize((size_t)C * n);
+    for (size_t i = 0; i < (size_t)C * n; i++) b->coeffs[i] = gl_canon(coeffs[i]);
+    if (orc_batch_from_coeffs(*b, cap_height)) { delete b; return nullptr; }
+    return b;
+}
+void orc_batch_free(void *h) { delete (OrcBatch *)h; }
+const u64 *orc_batch_coeffs(void *h) { return ((OrcBatch *)h)->coeffs.data(); }
+const u64 *orc_batch_leaves(void *h) { return ((OrcBatch *)h)->tree.leaves.data(); }
+const u64 *orc_batch_digests(void *h) { return ((OrcBatch *)h)->tree.digests.data(); }
+size_t orc_batch_num_digests(void *h) { return ((OrcBatch *)h)->tree.digests.size() / 4; }
+const u64 *orc_batch_cap(void *h) { return ((OrcBatch *)h)->tree.cap.data(); }
+int orc_batch_prove(void *h, size_t leaf_index, u64 *siblings) { return orc_merkle_prove(((OrcBatch *)h)->tree, leaf_index, siblings); }
+void orc_batch_times(void *h, double *out4) {
+    OrcBatch *b = (OrcBatch *)h;
+    out4[0] = b->t_ifft; out4[1] = b->t_lde; out4[2] = b->t_transpose; out4[3] = b->t_tree;
+}
+
+/* ---- bare MerkleTree::new over row-major leaves ---- */
+void *orc_merkle_new(const u64 *leaves, size_t num_leaves, size_t leaf_len, int cap_height) {
+    OrcBatch *b = new OrcBatch();
+    b->tree.num_leaves = num_leaves; b->tree.leaf_len = leaf_len; b->tree.cap_height = cap_height;
+    b->tree.leaves.resize(num_leaves * leaf_len);
+    for (size_t i = 0; i < num_leaves * leaf_len; i++) b->tree.leaves[i] = gl_canon(leaves[i]);
+    if (orc_merkle_build(b->tree)) { delete b; return nullptr; }
+    return b;
+}
+int orc_merkle_verify_c(const u64 *leaf, size_t leaf_len, size_t leaf_index, const u64 *cap, const u64 *siblings, int n) {
+    return orc_merkle_verify(leaf, leaf_len, leaf_index, cap, siblings, n);
+}
+
+/* ---- Challenger ---- */
+void *orc_challenger_new() { OrcChallenger *c = new OrcChallenger(); orc_ch_init(c); return c; }
+void orc_challenger_free(void *c) { delete (OrcChallenger *)c; }
+void orc_challenger_observe(void *c, const u64 *e, size_t n) { orc_ch_observe_n((OrcChallenger *)c, e, n); }
+u64 orc_challenger_get(void *c) { return orc_ch_challenge((OrcChallenger *)c); }
+
+} /* extern "C" */

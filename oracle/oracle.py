@@ -1,0 +1,212 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY (see oracle/gl.h).
+
+A C++ restatement of plonky2 0.1.4's commit path.  Builds itself with `make`
+on first use if the shared object is missing.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+P = 0xFFFFFFFF00000001
+
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".h", ".cpp"))]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_poseidon_permute.argtypes = [_u64p, C.c_int]
+        L.orc_hash_n.argtypes = [_u64p, C.c_size_t, _u64p, C.c_int]
+        L.orc_compress.argtypes = [_u64p, _u64p, _u64p]
+        for f in (L.orc_gl_mul, L.orc_gl_pow):
+            f.restype = C.c_uint64; f.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_gl_inv.restype = C.c_uint64; L.orc_gl_inv.argtypes = [C.c_uint64]
+        L.orc_root_of_unity.restype = C.c_uint64; L.orc_root_of_unity.argtypes = [C.c_int]
+        L.orc_fft.argtypes = [_u64p, C.c_int]
+        L.orc_ifft.argtypes = [_u64p, C.c_int]
+        L.orc_lde.argtypes = [_u64p, C.c_int, C.c_int, C.c_uint64, _u64p]
+        for f in (L.orc_batch_from_values_c, L.orc_batch_from_coeffs_c):
+            f.restype = C.c_void_p; f.argtypes = [_u64p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_batch_free.argtypes = [C.c_void_p]
+        for f in (L.orc_batch_coeffs, L.orc_batch_leaves, L.orc_batch_digests, L.orc_batch_cap):
+            f.restype = C.POINTER(C.c_uint64); f.argtypes = [C.c_void_p]
+        L.orc_batch_num_digests.restype = C.c_size_t; L.orc_batch_num_digests.argtypes = [C.c_void_p]
+        L.orc_batch_prove.restype = C.c_int; L.orc_batch_prove.argtypes = [C.c_void_p, C.c_size_t, _u64p]
+        L.orc_batch_times.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.float64)]
+        L.orc_merkle_new.restype = C.c_void_p; L.orc_merkle_new.argtypes = [_u64p, C.c_size_t, C.c_size_t, C.c_int]
+        L.orc_merkle_verify_c.restype = C.c_int
+        L.orc_merkle_verify_c.argtypes = [_u64p, C.c_size_t, C.c_size_t, _u64p, _u64p, C.c_int]
+        L.orc_challenger_new.restype = C.c_void_p
+        L.orc_challenger_free.argtypes = [C.c_void_p]
+        L.orc_challenger_observe.argtypes = [C.c_void_p, _u64p, C.c_size_t]
+        L.orc_challenger_get.restype = C.c_uint64; L.orc_challenger_get.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _a(x):
+    return np.ascontiguousarray(x, dtype=np.uint64)
+
+
+def poseidon(state, naive=False):
+    s = _a(state).copy()
+    assert s.shape == (12,)
+    lib().orc_poseidon_permute(s, int(naive))
+    return s
+
+
+def hash_no_pad(xs):
+    out = np.zeros(4, np.uint64); xs = _a(xs)
+    lib().orc_hash_n(xs, xs.size, out, 0)
+    return out
+
+
+def hash_or_noop(xs):
+    out = np.zeros(4, np.uint64); xs = _a(xs)
+    lib().orc_hash_n(xs, xs.size, out, 1)
+    return out
+
+
+def two_to_one(l, r):
+    out = np.zeros(4, np.uint64)
+    lib().orc_compress(_a(l), _a(r), out)
+    return out
+
+
+def fft(a):
+    a = _a(a).copy(); lib().orc_fft(a, int(a.size).bit_length() - 1); return a
+
+
+def ifft(a):
+    a = _a(a).copy(); lib().orc_ifft(a, int(a.size).bit_length() - 1); return a
+
+
+def lde(coeffs, rate_bits, shift=7):
+    coeffs = _a(coeffs); log_n = int(coeffs.size).bit_length() - 1
+    out = np.zeros(coeffs.size << rate_bits, np.uint64)
+    lib().orc_lde(coeffs, log_n, rate_bits, shift, out)
+    return out
+
+
+class Batch:
+    """PolynomialBatch as computed by the oracle: coeffs [C][n], leaves [L][C], digests, cap."""
+
+    def __init__(self, handle, C_, log_n, rate_bits, cap_height):
+        if not handle:
+            raise ValueError("oracle: MerkleTree::new precondition violated (cap_height > log2(leaves))")
+        self.h, self.C, self.log_n, self.rate_bits, self.cap_height = handle, C_, log_n, rate_bits, cap_height
+        self.n = 1 << log_n
+        self.L = self.n << rate_bits
+
+    @classmethod
+    def from_values(cls, values, rate_bits, cap_height):
+        values = _a(values); C_, n = values.shape
+        log_n = n.bit_length() - 1
+        return cls(lib().orc_batch_from_values_c(values, C_, log_n, rate_bits, cap_height), C_, log_n, rate_bits, cap_height)
+
+    @classmethod
+    def from_coeffs(cls, coeffs, rate_bits, cap_height):
+        coeffs = _a(coeffs); C_, n = coeffs.shape
+        log_n = n.bit_length() - 1
+        return cls(lib().orc_batch_from_coeffs_c(coeffs, C_, log_n, rate_bits, cap_height), C_, log_n, rate_bits, cap_height)
+
+    def _view(self, ptr, shape):
+        return np.ctypeslib.as_array(ptr, shape=shape)
+
+    @property
+    def coeffs(self):
+        return self._view(lib().orc_batch_coeffs(self.h), (self.C, self.n))
+
+    @property
+    def leaves(self):
+        return self._view(lib().orc_batch_leaves(self.h), (self.L, self.C))
+
+    @property
+    def digests(self):
+        nd = lib().orc_batch_num_digests(self.h)
+        if nd == 0:
+            return np.zeros((0, 4), np.uint64)
+        return self._view(lib().orc_batch_digests(self.h), (nd, 4))
+
+    @property
+    def cap(self):
+        return self._view(lib().orc_batch_cap(self.h), (1 << self.cap_height, 4))
+
+    def prove(self, leaf_index):
+        sib = np.zeros((64, 4), np.uint64)
+        k = lib().orc_batch_prove(self.h, leaf_index, sib)
+        return sib[:k].copy()
+
+    def times(self):
+        t = np.zeros(4); lib().orc_batch_times(self.h, t)
+        return dict(ifft=t[0], lde=t[1], transpose=t[2], tree=t[3])
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_batch_free(self.h); self.h = None
+
+
+class MerkleTree(Batch):
+    def __init__(self, leaves, cap_height):
+        leaves = _a(leaves); L, w = leaves.shape
+        h = lib().orc_merkle_new(leaves, L, w, cap_height)
+        if not h:
+            raise ValueError("oracle: MerkleTree::new precondition violated (cap_height > log2(leaves))")
+        self.h, self.C, self.L, self.cap_height = h, w, L, cap_height
+        self.n, self.log_n, self.rate_bits = L, L.bit_length() - 1, 0
+
+
+def merkle_verify(leaf, leaf_index, cap, siblings):
+    leaf = _a(leaf); siblings = _a(siblings).reshape(-1, 4)
+    return bool(lib().orc_merkle_verify_c(leaf, leaf.size, leaf_index, _a(cap), siblings, siblings.shape[0]))
+
+
+class Challenger:
+    def __init__(self):
+        self.h = lib().orc_challenger_new()
+
+    def observe(self, xs):
+        xs = _a(np.atleast_1d(xs)).ravel(); lib().orc_challenger_observe(self.h, xs, xs.size)
+
+    def get_challenge(self):
+        return int(lib().orc_challenger_get(self.h))
+
+    def get_n_challenges(self, n):
+        return [self.get_challenge() for _ in range(n)]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_challenger_free(self.h); self.h = None
+
+
+def splitmix_columns(C_, n, seed=0x9E3779B97F4A7C15):
+    """Synthetic witness of SURVEY.md 8(d): values[c][i] = SplitMix64(seed ^ c) step i, reduced mod p."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    out = np.empty((C_, n), np.uint64)
+    steps = (np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+    with np.errstate(over="ignore"):
+        for c in range(C_):
+            z = np.uint64(seed ^ c) + steps
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            out[c] = np.where(z >= np.uint64(P), z - np.uint64(P), z)
+    return out

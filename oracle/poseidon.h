@@ -1,0 +1,118 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY (see gl.h header).
+ *
+ * Poseidon permutation over Goldilocks and the sponge built on it.
+ * Restates [DEP plonky2:hash/poseidon.rs, hash/poseidon_goldilocks.rs, hash/hashing.rs].
+ * PINNED: the permutation reproduces the 4 upstream known-answer vectors in both the
+ * naive form and the fast-partial-round form (tests/test_oracle.py).  The sponge MODE (overwrite, rate 8, no
+ * padding) is restated from the published algorithm: parity unpinned.
+ */
+#ifndef ORACLE_POSEIDON_H
+#define ORACLE_POSEIDON_H
+#include "gl.h"
+#include "poseidon_consts.h"
+
+static const u64 ORC_MDS_CIRC[12] = POSEIDON_MDS_CIRC_INIT;
+
+static inline u64 orc_sbox7(u64 x) {
+    u64 x2 = gl_sqr(x), x4 = gl_sqr(x2), x3 = gl_mul(x, x2);
+    return gl_mul(x3, x4);
+}
+
+/* out[r] = sum_i in[(i+r)%12]*CIRC[i] + in[r]*DIAG[r]   [poseidon.rs::mds_layer] */
+static inline void orc_mds(u64 s[12]) {
+    u64 o[12];
+    for (int r = 0; r < 12; r++) {
+        u128 acc = 0;
+        for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * ORC_MDS_CIRC[i];
+        if (r == 0) acc += (u128)s[0] * POSEIDON_MDS_DIAG0;
+        o[r] = gl_reduce128(acc);
+    }
+    for (int r = 0; r < 12; r++) s[r] = o[r];
+}
+
+/* Reference ("naive") form: every round adds 12 constants, S-box (all lanes / lane 0), MDS. */
+static inline void orc_poseidon_naive(u64 s[12]) {
+    for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
+    int rnd = 0;
+    for (int ph = 0; ph < 3; ph++) {
+        int n = ph == 1 ? POSEIDON_PARTIAL_ROUNDS : POSEIDON_HALF_FULL_ROUNDS;
+        for (int k = 0; k < n; k++, rnd++) {
+            for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POSEIDON_RC[12 * rnd + i]);
+            if (ph == 1) s[0] = orc_sbox7(s[0]);
+            else for (int i = 0; i < 12; i++) s[i] = orc_sbox7(s[i]);
+            orc_mds(s);
+        }
+    }
+}
+
+/* Production form of plonky2 (partial rounds through the sparse factorisation); identical outputs. */
+static inline void orc_poseidon(u64 s[12]) {
+    for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
+    int rnd = 0;
+    for (int k = 0; k < 4; k++, rnd++) {
+        for (int i = 0; i < 12; i++) s[i] = orc_sbox7(gl_add(s[i], POSEIDON_RC[12 * rnd + i]));
+        orc_mds(s);
+    }
+    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POSEIDON_FAST_FIRST[i]);
+    {
+        u64 o[11];
+        for (int i = 0; i < 11; i++) {
+            u128 acc = 0; u64 carry = 0;
+            for (int j = 0; j < 11; j++) {
+                u128 t = (u128)POSEIDON_FAST_INIT[11 * i + j] * s[j + 1];
+                acc += t; carry += acc < t;
+            }
+            /* acc + carry*2^128 ; 2^128 = 2^64*2^64 = eps^2 mod p */
+            u64 r = gl_reduce128(acc);
+            if (carry) r = gl_add(r, gl_mul(carry, gl_mul(GL_EPS, GL_EPS)));
+            o[i] = r;
+        }
+        for (int i = 0; i < 11; i++) s[i + 1] = o[i];
+    }
+    for (int r = 0; r < POSEIDON_PARTIAL_ROUNDS; r++) {
+        u64 s0 = gl_add(orc_sbox7(s[0]), POSEIDON_FAST_K[r]);
+        u128 acc = (u128)s0 * 25; u64 carry = 0;
+        for (int i = 0; i < 11; i++) {
+            u128 t = (u128)POSEIDON_FAST_ROW[11 * r + i] * s[i + 1];
+            acc += t; carry += acc < t;
+        }
+        u64 d = gl_reduce128(acc);
+        if (carry) d = gl_add(d, gl_mul(carry, gl_mul(GL_EPS, GL_EPS)));
+        for (int i = 0; i < 11; i++) s[i + 1] = gl_add(s[i + 1], gl_mul(POSEIDON_FAST_COL[11 * r + i], s0));
+        s[0] = d;
+    }
+    rnd += POSEIDON_PARTIAL_ROUNDS;
+    for (int k = 0; k < 4; k++, rnd++) {
+        for (int i = 0; i < 12; i++) s[i] = orc_sbox7(gl_add(s[i], POSEIDON_RC[12 * rnd + i]));
+        orc_mds(s);
+    }
+}
+
+/* hash_n_to_m_no_pad with m = 4: overwrite-mode sponge, rate 8 [hashing.rs] */
+static inline void orc_hash_no_pad(const u64 *in, size_t n, u64 out[4]) {
+    u64 s[12] = {0};
+    for (size_t off = 0; off < n; off += 8) {
+        size_t len = n - off < 8 ? n - off : 8;
+        for (size_t i = 0; i < len; i++) s[i] = gl_canon(in[off + i]);
+        orc_poseidon(s);
+    }
+    for (int i = 0; i < 4; i++) out[i] = s[i];
+}
+
+/* hash_or_noop: <= 4 elements are zero-padded into the digest without hashing [hashing.rs / config.rs] */
+static inline void orc_hash_or_noop(const u64 *in, size_t n, u64 out[4]) {
+    if (n <= 4) {
+        for (size_t i = 0; i < 4; i++) out[i] = i < n ? gl_canon(in[i]) : 0;
+    } else {
+        orc_hash_no_pad(in, n, out);
+    }
+}
+
+/* two_to_one = permute([l, r, 0,0,0,0])[0..4] [hashing.rs::compress] */
+static inline void orc_two_to_one(const u64 l[4], const u64 r[4], u64 out[4]) {
+    u64 s[12] = {l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], 0, 0, 0, 0};
+    orc_poseidon(s);
+    for (int i = 0; i < 4; i++) out[i] = s[i];
+}
+
+#endif
