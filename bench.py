@@ -1,0 +1,290 @@
+#!/usr/bin/env python3
+"""bench.py -- commit-phase throughput of the B200 plonky2 engine (BASELINE.json configs[1]).
+
+A step = one PolynomialBatch::from_values over synthetic witness columns: iNTT -> coset LDE (rate_bits 3) ->
+Poseidon leaf hashing -> digest tree -> cap (cap_height 4).  Workload at N=1: 135 Goldilocks columns x 2^20 rows.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log-n 20] [--cols 135]
+
+metric  commit_throughput [GB/s] = algorithmic commit bytes B_ntt = 8*C*n*(2 + 2^rate_bits) per step / time
+        (read the values once, write the coefficients once, write the LDE once).
+value   inputs already resident in HBM, timed with CUDA events on the engine's stream.
+e2e     the same commit through the reference-facing C-ABI call with HOST buffers (eng_batch_from_values with
+        pinned host columns; H2D copies and the D2H read of the cap inside the timed region).
+roofline       the dominant kernel (Poseidon leaf hashing): integer-pipe bound, 6,612 IMAD32 per permutation.
+roofline_hbm   the NTT/LDE kernels against the measured HBM copy bandwidth.
+cpu_baseline   the C++/OpenMP oracle (a restatement of plonky2's CPU algorithm -- the Rust prover itself cannot be
+               built here) timed on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RATE_BITS = 3
+CAP_HEIGHT = 4
+IMAD_PER_PERM = 6612
+NOMINAL_IMAD_PER_S = 148 * 64 * 1.965e9   # 64 IMAD/clk/SM; no integer entry in MEASURED_PEAKS.json
+
+
+def b_ntt(cols, n, rate_bits=RATE_BITS):
+    return 8 * cols * n * (2 + (1 << rate_bits))
+
+
+def num_perms(cols, n, rate_bits=RATE_BITS, cap_height=CAP_HEIGHT):
+    L = n << rate_bits
+    return L * ((cols + 7) // 8) + (L - (1 << cap_height))
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_commit(cols, log_n, threads=None):
+    """Times the CPU oracle on one commit; returns (seconds, stage dict, threads)."""
+    from oracle import oracle as O
+    if threads:
+        O.lib().orc_set_num_threads(threads)
+    vals = O.splitmix_columns(cols, 1 << log_n)
+    t0 = time.perf_counter()
+    b = O.Batch.from_values(vals, RATE_BITS, CAP_HEIGHT)
+    dt = time.perf_counter() - t0
+    stages = b.times()
+    del b
+    return dt, stages, O.lib().orc_num_threads()
+
+
+def cpu_sample_log_n(cols, target_s=12.0, max_log_n=18):
+    """Largest sample (rows = 2^k <= 2^max_log_n) whose commit should take about target_s on this host."""
+    dt, _, _ = cpu_commit(cols, 12)
+    per_row = dt / (1 << 12)
+    k = 12
+    while k < max_log_n and per_row * (1 << (k + 1)) <= target_s:
+        k += 1
+    return k
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores, same metric / config / unit.
+    The reference's own Rust prover cannot be built here (no cargo/rustc, plonky2 not vendored): the timed code is
+    the oracle port (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cols = args.cols
+    k = min(args.log_n, cpu_sample_log_n(cols, target_s=max(4.0, 40.0 / max(1, args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        cpu_commit(cols, k)
+    t = []
+    stages, threads = {}, 1
+    for _ in range(args.steps):
+        dt, stages, threads = cpu_commit(cols, k)
+        t.append(dt)
+    sec = sum(t) / len(t)
+    gbs = b_ntt(cols, 1 << k) / sec / 1e9
+    line = {
+        "impl": "reference", "metric": "commit_throughput", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic (SplitMix64 witness columns)",
+        "config": workload_config(cols, args.log_n, args.gpus),
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
+                         "sample": "one PolynomialBatch::from_values of %d columns x 2^%d rows (rate_bits 3, cap_height 4) per step; "
+                                   "C++/OpenMP restatement of plonky2's CPU algorithm, not the Rust prover" % (cols, k),
+                         "stage_s": stages},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(cols, log_n, gpus):
+    return {"workload": "PolynomialBatch::from_values commit, %d Goldilocks columns x 2^%d rows, rate_bits=3, cap_height=4 "
+                        "(BASELINE.json configs[1])" % (cols, log_n),
+            "columns": cols, "log_rows": log_n, "rate_bits": RATE_BITS, "cap_height": CAP_HEIGHT,
+            "parallelism": "1 GPU" if gpus == 1 else "%d GPUs, one batch per rank (weak)" % gpus,
+            "l2": "inputs (%.2f GB per step) are larger than the 126 MB L2; no flush needed" % (8 * cols * (1 << log_n) / 1e9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--cols", type=int, default=135)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import eth_lc_plonky2_b200 as E
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    distributed = world > 1
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    E.init(local_rank)
+    stream = torch.cuda.Stream()
+    E.set_stream(stream.cuda_stream)
+
+    cols, log_n = args.cols, args.log_n
+    n = 1 << log_n
+    # synthetic witness, generated on the host, pinned for the e2e path
+    host = torch.from_numpy(E.splitmix_columns(cols, n, seed=0x9E3779B97F4A7C15 + rank).view(np.int64)).pin_memory()
+    dev = host.cuda(non_blocking=False)
+    host_np = host.numpy().view(np.uint64)
+    host_cols = [host_np[c] for c in range(cols)]
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        b = E.PolynomialBatch.from_values(dev, RATE_BITS, False, CAP_HEIGHT)
+        ms = b.stage_ms()
+        b.close()
+        return ms
+
+    def step_e2e():
+        b = E.PolynomialBatch.from_values(host_cols, RATE_BITS, False, CAP_HEIGHT)
+        cap = b.merkle_tree.cap            # D2H read of the result
+        b.close()
+        return cap
+
+    # ---- device-resident arm ----
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = E.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_acc = {}
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            for k, v in step_device().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+        ev1.record(stream)
+    barrier()
+    launches = E.launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.summary()
+
+    # ---- end-to-end arm (host buffers through the C ABI) ----
+    for _ in range(max(1, min(args.warmup, 2))):
+        cap_e2e = step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            cap_e2e = step_e2e()
+        e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = times.tolist()
+
+    int_peak = E.measure_int_peak()
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        bytes_step = b_ntt(cols, n) * world
+        ms_step = ms_total / args.steps
+        value = bytes_step / (ms_step * 1e-3) / 1e9
+        e2e_value = bytes_step / (ms_e2e / args.steps * 1e-3) / 1e9
+        stages = {k: v / args.steps for k, v in stage_acc.items()}
+        leaf_ms = stages["build Merkle tree (leaves)"]
+        L = n << RATE_BITS
+        leaf_perms = L * ((cols + 7) // 8)
+        imad_rate = leaf_perms * IMAD_PER_PERM / (leaf_ms * 1e-3)
+        ntt_ms = stages["IFFT"] + stages["FFT + blinding"]
+        hbm_rate = b_ntt(cols, n) / (ntt_ms * 1e-3) / 1e9
+        line = {
+            "metric": "commit_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic (SplitMix64 witness columns)",
+            "config": workload_config(cols, log_n, world),
+            "e2e": {"value": e2e_value, "unit": "GB/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 8 * cols * n, "d2h_bytes_per_step": 32 << CAP_HEIGHT},
+            "gpu_launches": launches,
+            "stage_ms": stages,
+            "roofline": {"kernel": "merkle_leaves_kernel (Poseidon leaf hashing, %d permutations per launch)" % leaf_perms,
+                         "bound": "int32-imad", "achieved": imad_rate / 1e12, "peak": NOMINAL_IMAD_PER_S / 1e12,
+                         "unit": "TIMAD32/s", "frac": imad_rate / NOMINAL_IMAD_PER_S, "traffic": None,
+                         "peak_kind": "nominal 148 SM x 64 IMAD/clk x 1.965 GHz (no measured integer peak in MEASURED_PEAKS.json)",
+                         "perms_per_s": leaf_perms / (leaf_ms * 1e-3), "kernel_ms": leaf_ms,
+                         "measured_issue_rates_Tops": {k: v / 1e12 for k, v in int_peak.items()},
+                         "frac_of_measured_imad": imad_rate / int_peak["imad"]},
+            "roofline_hbm": {"kernel": "ntt_pass_kernel x4 (iNTT 2 passes + coset LDE 2 passes)", "bound": "hbm",
+                             "achieved": hbm_rate, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_rate / peaks["hbm_gbs"],
+                             "traffic": None, "peak_kind": peak_kind, "kernel_ms": ntt_ms, "algorithmic_bytes": b_ntt(cols, n)},
+            "clocks": clocks,
+            "cap0": "%016x" % int(cap_e2e[0][0]),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            k = cpu_sample_log_n(cols)
+            dt, cpu_stages, threads = cpu_commit(cols, k)
+            line["cpu_baseline"] = {"value": b_ntt(cols, 1 << k) / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+                                    "sample": "one commit of %d columns x 2^%d rows (rate_bits 3, cap_height 4), %.1f s; C++/OpenMP "
+                                              "restatement of plonky2's CPU algorithm, not the Rust prover" % (cols, k, dt),
+                                    "stage_s": cpu_stages}
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

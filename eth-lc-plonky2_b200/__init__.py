@@ -1,0 +1,16 @@
+"""B200-native plonky2 commitment engine for the eth-lc-plonky2 light-client circuit.
+
+The product is libplonky2_b200.so (CUDA kernels for sm_100a behind the C ABI of include/plonky2_b200.h);
+this package is the thin host-side mirror of the plonky2 operator surface used by tests, bench.py and the
+torch.distributed plumbing.  There is no CPU path.
+"""
+from . import build as _build_mod
+from ._lib import (ENG_ERR_CUDA, ENG_ERR_INVALID, ENG_ERR_OOM, ENG_ERR_STATE, ENG_OK, EngineError, exported_symbols, init,
+                   launch_count, load, measure_int_peak, set_stream, so_path, synchronize)
+from .synthetic import splitmix_columns
+from .plonky2 import SALT_SIZE, MerkleTree, PolynomialBatch, PoseidonHash, poseidon
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA extension in-tree for sm_100a."""
+    return _build_mod.build(force=force, verbose=verbose)

@@ -1,0 +1,648 @@
+// libplonky2_b200.so -- engine context, device-resident PolynomialBatch handles and the C ABI of
+// include/plonky2_b200.h.  Host orchestration only; the arithmetic lives in ntt.cuh / merkle.cuh / poseidon.cuh.
+//
+// Replaces, for the hot path, plonky2::fri::oracle::PolynomialBatch::{from_values, from_coeffs, get_lde_values} and
+// plonky2::hash::merkle_tree::MerkleTree::{new, get, prove} (dep plonky2 0.1.4, /root/reference/Cargo.lock:2347-2350),
+// reached from /root/reference/eth-lc-plonky2/src/main.rs:227 (build) and :230 (prove).
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/plonky2_b200.h"
+#include "merkle.cuh"
+#include "microbench.cuh"
+#include "ntt.cuh"
+#include "ntt_plan.h"
+
+#define SALT_SIZE 4u
+
+namespace {
+
+thread_local std::string g_err;
+std::recursive_mutex g_mu;
+
+eng_status fail(eng_status code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? ENG_ERR_OOM : ENG_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+    } while (0)
+#define ST(call)                         \
+    do {                                 \
+        eng_status s_ = (call);          \
+        if (s_ != ENG_OK) return s_;     \
+    } while (0)
+
+struct Ctx {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    NttTableStore tables;
+    std::vector<void *> table_allocs;
+    uint64_t launches = 0;
+    cudaEvent_t ev[8] = {};
+};
+Ctx g;
+
+}  // namespace
+
+struct eng_batch {
+    uint32_t num_polys = 0, degree_log = 0, rate_bits = 0, cap_height = 0, blinding = 0, leaf_len = 0;
+    uint64_t num_leaves = 0, num_digests = 0;
+    uint32_t num_layers = 0;
+    u64 *coeffs = nullptr;       // [num_polys][n]
+    u64 *lde = nullptr;          // [leaf_len][num_leaves] column-major, bit-reversed rows (owned)
+    const u64 *leaf_data = nullptr;  // what the tree was built over
+    u64 row_stride = 0, col_stride = 0;
+    u64 *digests = nullptr, *cap = nullptr;
+    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+__global__ void salt_kernel(u64 *dst, u64 count, u64 seed) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    dst[i] = gl_canon(z);
+}
+__global__ void permute_kernel(const u64 *in, u64 *out, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = in[12 * i + k];
+    poseidon_permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) out[12 * i + k] = gl_canon(s[k]);
+}
+__global__ void two_to_one_kernel(const u64 *pairs, u64 *out, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 d[4];
+    poseidon_two_to_one(pairs + 8 * i, pairs + 8 * i + 4, d);
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[4 * i + k] = d[k];
+}
+// rows [first, first+count) of the leaf matrix -> row-major out[count][width]
+__global__ void gather_rows_kernel(const u64 *data, u64 row_stride, u64 col_stride, u32 width, u64 first, u64 count,
+                                   u64 *out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * width) return;
+    u64 r = i / width, c = i % width;
+    out[i] = gl_canon(data[(first + r) * row_stride + c * col_stride]);
+}
+
+eng_status dev_alloc(u64 **p, size_t elems) {
+    *p = nullptr;
+    if (elems == 0) return ENG_OK;
+    cudaError_t e = cudaMallocAsync((void **)p, elems * sizeof(u64), g.stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ENG_ERR_OOM, "device allocation of %zu bytes failed: %s", elems * sizeof(u64), cudaGetErrorString(e));
+    }
+    return ENG_OK;
+}
+void dev_free(void *p) {
+    if (p) cudaFreeAsync(p, g.stream);
+}
+
+template <int MODE>
+eng_status launch_mode(const NttLaunch &l) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(ntt_pass_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ntt_pass_kernel<MODE>, (int)l.threads, l.smem));
+    if (per_sm < 1) return fail(ENG_ERR_CUDA, "NTT pass (log_p=%u log_a=%u) does not fit on an SM", l.p.log_p, l.p.log_a);
+    u64 grid = (u64)g.sm_count * per_sm;
+    if (grid > l.p.num_tiles) grid = l.p.num_tiles;
+    if (grid == 0) return ENG_OK;
+    ntt_pass_kernel<MODE><<<(unsigned)grid, l.threads, l.smem, g.stream>>>(l.p);
+    g.launches++;
+    CU(cudaGetLastError());
+    return ENG_OK;
+}
+eng_status launch_plan(const std::vector<NttLaunch> &plan) {
+    for (const NttLaunch &l : plan) {
+        switch (l.mode) {
+            case NTT_LDE_FIRST: ST(launch_mode<NTT_LDE_FIRST>(l)); break;
+            case NTT_LDE_SINGLE: ST(launch_mode<NTT_LDE_SINGLE>(l)); break;
+            case NTT_DIF_LAST: ST(launch_mode<NTT_DIF_LAST>(l)); break;
+            case NTT_INTT_P1: ST(launch_mode<NTT_INTT_P1>(l)); break;
+            case NTT_INTT_P2: ST(launch_mode<NTT_INTT_P2>(l)); break;
+            case NTT_INTT_SINGLE: ST(launch_mode<NTT_INTT_SINGLE>(l)); break;
+            default: return fail(ENG_ERR_INVALID, "unknown NTT pass mode %d", l.mode);
+        }
+    }
+    return ENG_OK;
+}
+
+// MerkleTree::new over b->leaf_data; fills digests and cap.
+eng_status build_tree(eng_batch *b) {
+    MerkleParams mp;
+    mp.data = b->leaf_data; mp.row_stride = b->row_stride; mp.col_stride = b->col_stride;
+    mp.width = b->leaf_len; mp.num_leaves = b->num_leaves; mp.num_layers = b->num_layers;
+    mp.digests = b->digests; mp.cap = b->cap;
+    mp.noop_max = 4;  // H::hash_or_noop
+    CU(cudaEventRecord(g.ev[3], g.stream));
+    {
+        unsigned threads = 128;
+        u64 blocks = (b->num_leaves + threads - 1) / threads;
+        merkle_leaves_kernel<<<(unsigned)blocks, threads, 0, g.stream>>>(mp);
+        g.launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(g.ev[4], g.stream));
+    for (u32 layer = 0; layer < b->num_layers; layer++) {
+        u64 parents = b->num_leaves >> (layer + 1);
+        unsigned threads = 128;
+        u64 blocks = (parents + threads - 1) / threads;
+        merkle_level_kernel<<<(unsigned)blocks, threads, 0, g.stream>>>(mp, layer);
+        g.launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(g.ev[5], g.stream));
+    return ENG_OK;
+}
+
+eng_status check_ready() {
+    if (!g.ready) return fail(ENG_ERR_STATE, "engine not initialised: call eng_init(device) on a machine with a CUDA device");
+    return ENG_OK;
+}
+
+eng_status collect_times(eng_batch *b, bool had_ifft, bool had_lde) {
+    CU(cudaStreamSynchronize(g.stream));
+    float ms = 0;
+    if (had_ifft) { CU(cudaEventElapsedTime(&ms, g.ev[1], g.ev[2])); b->stage_ms[0] = ms; }
+    if (had_lde) { CU(cudaEventElapsedTime(&ms, g.ev[2], g.ev[3])); b->stage_ms[1] = ms; }
+    CU(cudaEventElapsedTime(&ms, g.ev[3], g.ev[4])); b->stage_ms[3] = ms;
+    CU(cudaEventElapsedTime(&ms, g.ev[4], g.ev[5])); b->stage_ms[4] = ms;
+    if (had_ifft || had_lde) { CU(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1])); b->stage_ms[5] = ms; }
+    return ENG_OK;
+}
+
+void destroy_batch(eng_batch *b) {
+    if (!b) return;
+    dev_free(b->coeffs); dev_free(b->lde); dev_free(b->digests); dev_free(b->cap);
+    delete b;
+}
+
+// Shared tail of from_values / from_coeffs.  `src` holds values (is_values) or coefficients, either as C host
+// column pointers (cols_host) or as one device array [C][n] (src_dev).
+eng_status make_batch(const uint64_t *const *cols_host, const u64 *src_dev, bool is_values, uint32_t C, uint32_t log_n,
+                      uint32_t rate_bits, int32_t blinding, uint64_t seed, uint32_t cap_height, eng_batch **out) {
+    ST(check_ready());
+    if (!out) return fail(ENG_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (C == 0) return fail(ENG_ERR_INVALID, "PolynomialBatch needs at least one polynomial");
+    if (log_n > 2 * NTT_MAX_LOGP) return fail(ENG_ERR_INVALID, "degree_log %u > %d unsupported", log_n, 2 * NTT_MAX_LOGP);
+    if (log_n + rate_bits > 32) return fail(ENG_ERR_INVALID, "LDE size 2^%u exceeds the field's two-adicity", log_n + rate_bits);
+    if (cap_height > log_n + rate_bits)
+        return fail(ENG_ERR_INVALID, "cap_height %u > log2(leaves) %u (MerkleTree::new assertion)", cap_height, log_n + rate_bits);
+    if (!cols_host && !src_dev) return fail(ENG_ERR_INVALID, "input is NULL");
+
+    eng_batch *b = new eng_batch();
+    b->num_polys = C; b->degree_log = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    b->blinding = blinding ? 1 : 0;
+    b->leaf_len = C + (blinding ? SALT_SIZE : 0);
+    const u64 n = (u64)1 << log_n, L = n << rate_bits;
+    b->num_leaves = L;
+    b->num_layers = log_n + rate_bits - cap_height;
+    b->num_digests = 2 * (L - ((u64)1 << cap_height));
+    eng_status st;
+    if ((st = dev_alloc(&b->coeffs, (size_t)C * n)) != ENG_OK || (st = dev_alloc(&b->lde, (size_t)b->leaf_len * L)) != ENG_OK ||
+        (st = dev_alloc(&b->digests, (size_t)b->num_digests * 4)) != ENG_OK ||
+        (st = dev_alloc(&b->cap, (size_t)4 << cap_height)) != ENG_OK) {
+        destroy_batch(b);
+        return st;
+    }
+    b->leaf_data = b->lde; b->row_stride = 1; b->col_stride = L;
+
+    auto bail = [&](eng_status s) { destroy_batch(b); return s; };
+#define STB(call) do { eng_status s__ = (call); if (s__ != ENG_OK) return bail(s__); } while (0)
+#define CUB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(fail(ENG_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__))); } while (0)
+
+    CUB(cudaEventRecord(g.ev[0], g.stream));
+    const u64 *src = src_dev;
+    if (cols_host) {
+        for (uint32_t c = 0; c < C; c++) {
+            if (!cols_host[c]) return bail(fail(ENG_ERR_INVALID, "column %u is NULL", c));
+            CUB(cudaMemcpyAsync(b->coeffs + (size_t)c * n, cols_host[c], n * sizeof(u64), cudaMemcpyHostToDevice, g.stream));
+        }
+        src = b->coeffs;
+    }
+    CUB(cudaEventRecord(g.ev[1], g.stream));
+    std::vector<NttLaunch> plan;
+    if (is_values) {
+        // iNTT; the (not yet written) LDE buffer is the four-step scratch
+        if (!ntt_plan_intt(g.tables, src, n, b->lde, n, b->coeffs, n, C, log_n, plan)) return bail(fail(ENG_ERR_INVALID, "iNTT size unsupported"));
+        STB(launch_plan(plan));
+    } else if (src != b->coeffs) {
+        CUB(cudaMemcpyAsync(b->coeffs, src, (size_t)C * n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+    }
+    CUB(cudaEventRecord(g.ev[2], g.stream));
+    plan.clear();
+    if (!ntt_plan_lde(g.tables, b->coeffs, n, b->lde, L, C, log_n, rate_bits, plan)) return bail(fail(ENG_ERR_INVALID, "LDE size unsupported"));
+    STB(launch_plan(plan));
+    if (blinding) {
+        u64 count = (u64)SALT_SIZE * L;
+        salt_kernel<<<(unsigned)((count + 255) / 256), 256, 0, g.stream>>>(b->lde + (size_t)C * L, count, seed);
+        g.launches++;
+        CUB(cudaGetLastError());
+    }
+    STB(build_tree(b));
+    STB(collect_times(b, is_values, true));
+#undef STB
+#undef CUB
+    *out = b;
+    return ENG_OK;
+}
+
+eng_status d2h(void *dst, const void *src, size_t bytes) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    return ENG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+eng_status eng_init(int32_t device) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (g.ready) {
+        if (device != g.device) return fail(ENG_ERR_STATE, "engine already initialised on device %d", g.device);
+        return ENG_OK;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(ENG_ERR_STATE, "no CUDA device: %s (this engine has no CPU path)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return fail(ENG_ERR_INVALID, "device %d out of range [0, %d)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    g.device = device;
+    g.sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
+    for (auto &ev : g.ev) CU(cudaEventCreate(&ev));
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    CU(poseidon_upload_constants());
+    g.tables.upload = [](const std::vector<u64> &t) -> const u64 * {
+        void *d = nullptr;
+        if (cudaMalloc(&d, t.size() * sizeof(u64)) != cudaSuccess) return nullptr;
+        cudaMemcpy(d, t.data(), t.size() * sizeof(u64), cudaMemcpyHostToDevice);
+        g.table_allocs.push_back(d);
+        return (const u64 *)d;
+    };
+    g.launches = 0;
+    g.ready = true;
+    return ENG_OK;
+}
+
+eng_status eng_shutdown(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!g.ready) return ENG_OK;
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize();
+    for (void *p : g.table_allocs) cudaFree(p);
+    g.table_allocs.clear();
+    g.tables.tw_local_cache.clear(); g.tables.w2_cache.clear(); g.tables.shift_cache.clear();
+    for (auto &ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    if (g.own_stream) cudaStreamDestroy(g.own_stream);
+    g.own_stream = g.stream = nullptr;
+    g.ready = false;
+    return ENG_OK;
+}
+
+eng_status eng_last_error(char *buf, size_t len) {
+    if (!buf || len == 0) return ENG_ERR_INVALID;
+    snprintf(buf, len, "%s", g_err.c_str());
+    return ENG_OK;
+}
+
+eng_status eng_set_stream(void *cuda_stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    CU(cudaStreamSynchronize(g.stream));
+    g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own_stream;
+    return ENG_OK;
+}
+
+eng_status eng_synchronize(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    CU(cudaStreamSynchronize(g.stream));
+    return ENG_OK;
+}
+
+eng_status eng_launch_count(uint64_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!out) return ENG_ERR_INVALID;
+    *out = g.launches;
+    return ENG_OK;
+}
+
+eng_status eng_measure_int_peak(double *ops_per_s) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!ops_per_s) return fail(ENG_ERR_INVALID, "NULL argument");
+    uint32_t *d_out;
+    CU(cudaMalloc((void **)&d_out, 64));
+    const int iters = 4096, blocks = g.sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int kind = 0; kind < 3; kind++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            CU(cudaEventRecord(e0, g.stream));
+            if (kind == 0) int_peak_kernel<0><<<blocks, threads, 0, g.stream>>>(d_out, 12345u + rep, iters);
+            if (kind == 1) int_peak_kernel<1><<<blocks, threads, 0, g.stream>>>(d_out, 12345u + rep, iters);
+            if (kind == 2) int_peak_kernel<2><<<blocks, threads, 0, g.stream>>>(d_out, 12345u + rep, iters);
+            g.launches++;
+            CU(cudaEventRecord(e1, g.stream));
+            CU(cudaEventSynchronize(e1));
+            float ms;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        double ops = (double)blocks * threads * iters * 32.0 * (kind == 2 ? 2.0 : 1.0);
+        ops_per_s[kind] = ops / (best * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return ENG_OK;
+}
+
+eng_status eng_poseidon_permute(const uint64_t *states_host, uint64_t *out_host, size_t count) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (count == 0) return ENG_OK;
+    if (!states_host || !out_host) return fail(ENG_ERR_INVALID, "NULL buffer");
+    u64 *d_in, *d_out;
+    ST(dev_alloc(&d_in, count * 12));
+    ST(dev_alloc(&d_out, count * 12));
+    CU(cudaMemcpyAsync(d_in, states_host, count * 96, cudaMemcpyHostToDevice, g.stream));
+    permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, g.stream>>>(d_in, d_out, count);
+    g.launches++;
+    CU(cudaGetLastError());
+    eng_status s = d2h(out_host, d_out, count * 96);
+    dev_free(d_in); dev_free(d_out);
+    return s;
+}
+
+eng_status eng_hash_n(const uint64_t *in_host, size_t len, size_t count, int32_t or_noop, uint64_t *out_host) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (count == 0) return ENG_OK;
+    if ((!in_host && len) || !out_host) return fail(ENG_ERR_INVALID, "NULL buffer");
+    if (len >= (1ull << 32)) return fail(ENG_ERR_INVALID, "input too long");
+    u64 *d_in, *d_dig;
+    ST(dev_alloc(&d_in, count * (len ? len : 1)));
+    ST(dev_alloc(&d_dig, count * 4));
+    if (len) CU(cudaMemcpyAsync(d_in, in_host, count * len * 8, cudaMemcpyHostToDevice, g.stream));
+    // a zero-layer "tree" whose cap is the leaf digests: one sponge per row
+    MerkleParams mp;
+    mp.data = d_in; mp.row_stride = len; mp.col_stride = 1; mp.width = (u32)len; mp.num_leaves = count;
+    mp.num_layers = 0; mp.digests = nullptr; mp.cap = d_dig;
+    mp.noop_max = or_noop ? 4 : 0;  // hash_no_pad always runs the sponge (an empty input squeezes the zero state)
+    eng_status s = ENG_OK;
+    merkle_leaves_kernel<<<(unsigned)((count + 127) / 128), 128, 0, g.stream>>>(mp);
+    g.launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) s = fail(ENG_ERR_CUDA, "merkle_leaves_kernel: %s", cudaGetErrorString(e));
+    if (s == ENG_OK) s = d2h(out_host, d_dig, count * 32);
+    dev_free(d_in); dev_free(d_dig);
+    return s;
+}
+
+eng_status eng_two_to_one(const uint64_t *pairs_host, size_t count, uint64_t *out_host) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (count == 0) return ENG_OK;
+    if (!pairs_host || !out_host) return fail(ENG_ERR_INVALID, "NULL buffer");
+    u64 *d_in, *d_out;
+    ST(dev_alloc(&d_in, count * 8));
+    ST(dev_alloc(&d_out, count * 4));
+    CU(cudaMemcpyAsync(d_in, pairs_host, count * 64, cudaMemcpyHostToDevice, g.stream));
+    two_to_one_kernel<<<(unsigned)((count + 127) / 128), 128, 0, g.stream>>>(d_in, d_out, count);
+    g.launches++;
+    CU(cudaGetLastError());
+    eng_status s = d2h(out_host, d_out, count * 32);
+    dev_free(d_in); dev_free(d_out);
+    return s;
+}
+
+eng_status eng_batch_from_values(const uint64_t *const *cols_host, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits,
+                                 int32_t blinding, uint64_t blinding_seed, uint32_t cap_height, eng_batch **out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!cols_host) return fail(ENG_ERR_INVALID, "cols_host is NULL");
+    return make_batch(cols_host, nullptr, true, num_polys, log_n, rate_bits, blinding, blinding_seed, cap_height, out);
+}
+eng_status eng_batch_from_coeffs(const uint64_t *const *cols_host, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits,
+                                 int32_t blinding, uint64_t blinding_seed, uint32_t cap_height, eng_batch **out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!cols_host) return fail(ENG_ERR_INVALID, "cols_host is NULL");
+    return make_batch(cols_host, nullptr, false, num_polys, log_n, rate_bits, blinding, blinding_seed, cap_height, out);
+}
+eng_status eng_batch_from_values_dev(const uint64_t *values_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits,
+                                     int32_t blinding, uint64_t blinding_seed, uint32_t cap_height, eng_batch **out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!values_dev) return fail(ENG_ERR_INVALID, "values_dev is NULL");
+    return make_batch(nullptr, values_dev, true, num_polys, log_n, rate_bits, blinding, blinding_seed, cap_height, out);
+}
+eng_status eng_batch_from_coeffs_dev(const uint64_t *coeffs_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits,
+                                     int32_t blinding, uint64_t blinding_seed, uint32_t cap_height, eng_batch **out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!coeffs_dev) return fail(ENG_ERR_INVALID, "coeffs_dev is NULL");
+    return make_batch(nullptr, coeffs_dev, false, num_polys, log_n, rate_bits, blinding, blinding_seed, cap_height, out);
+}
+
+eng_status eng_batch_free(eng_batch *b) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!b) return ENG_OK;
+    ST(check_ready());
+    destroy_batch(b);
+    return ENG_OK;
+}
+
+static eng_status merkle_common(const u64 *data_dev, bool owned, u64 row_stride, u64 col_stride, uint64_t num_leaves,
+                                uint32_t leaf_len, uint32_t cap_height, eng_batch **out, u64 *owned_buf) {
+    u32 log_l = 0;
+    while (((u64)1 << log_l) < num_leaves) log_l++;
+    eng_batch *b = new eng_batch();
+    b->leaf_len = leaf_len; b->cap_height = cap_height; b->num_leaves = num_leaves;
+    b->degree_log = log_l; b->num_layers = log_l - cap_height;
+    b->num_digests = 2 * (num_leaves - ((u64)1 << cap_height));
+    if (owned) b->lde = owned_buf;
+    b->leaf_data = data_dev; b->row_stride = row_stride; b->col_stride = col_stride;
+    eng_status st;
+    if ((st = dev_alloc(&b->digests, (size_t)b->num_digests * 4)) != ENG_OK || (st = dev_alloc(&b->cap, (size_t)4 << cap_height)) != ENG_OK ||
+        (st = build_tree(b)) != ENG_OK || (st = collect_times(b, false, false)) != ENG_OK) {
+        destroy_batch(b);
+        return st;
+    }
+    *out = b;
+    return ENG_OK;
+}
+
+static eng_status merkle_check(uint64_t num_leaves, uint32_t leaf_len, uint32_t cap_height, eng_batch **out) {
+    ST(check_ready());
+    if (!out) return fail(ENG_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (num_leaves == 0 || (num_leaves & (num_leaves - 1))) return fail(ENG_ERR_INVALID, "number of leaves %llu is not a power of two (log2_strict)", (unsigned long long)num_leaves);
+    u32 log_l = 0;
+    while (((u64)1 << log_l) < num_leaves) log_l++;
+    if (cap_height > log_l) return fail(ENG_ERR_INVALID, "cap_height %u > log2(leaves) %u (MerkleTree::new assertion)", cap_height, log_l);
+    (void)leaf_len;
+    return ENG_OK;
+}
+
+eng_status eng_merkle_new(const uint64_t *leaves_host, uint64_t num_leaves, uint32_t leaf_len, uint32_t cap_height, eng_batch **out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(merkle_check(num_leaves, leaf_len, cap_height, out));
+    if (!leaves_host && leaf_len) return fail(ENG_ERR_INVALID, "leaves_host is NULL");
+    u64 *buf = nullptr;
+    ST(dev_alloc(&buf, (size_t)num_leaves * (leaf_len ? leaf_len : 1)));
+    CU(cudaEventRecord(g.ev[0], g.stream));
+    if (leaf_len) CU(cudaMemcpyAsync(buf, leaves_host, (size_t)num_leaves * leaf_len * 8, cudaMemcpyHostToDevice, g.stream));
+    return merkle_common(buf, true, leaf_len, 1, num_leaves, leaf_len, cap_height, out, buf);
+}
+
+eng_status eng_merkle_new_dev(const uint64_t *data_dev, uint64_t row_stride, uint64_t col_stride, uint64_t num_leaves,
+                              uint32_t leaf_len, uint32_t cap_height, eng_batch **out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(merkle_check(num_leaves, leaf_len, cap_height, out));
+    if (!data_dev && leaf_len) return fail(ENG_ERR_INVALID, "data_dev is NULL");
+    return merkle_common(data_dev, false, row_stride, col_stride, num_leaves, leaf_len, cap_height, out, nullptr);
+}
+
+eng_status eng_batch_info(const eng_batch *b, eng_batch_info_t *out) {
+    if (!b || !out) return fail(ENG_ERR_INVALID, "NULL argument");
+    out->num_polys = b->num_polys; out->degree_log = b->degree_log; out->rate_bits = b->rate_bits;
+    out->cap_height = b->cap_height; out->blinding = b->blinding; out->leaf_len = b->leaf_len;
+    out->num_leaves = b->num_leaves; out->num_digests = b->num_digests;
+    return ENG_OK;
+}
+
+eng_status eng_batch_cap(const eng_batch *b, uint64_t *out_host) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!b || !out_host) return fail(ENG_ERR_INVALID, "NULL argument");
+    return d2h(out_host, b->cap, (size_t)32 << b->cap_height);
+}
+
+eng_status eng_batch_digests(const eng_batch *b, uint64_t *out_host) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!b || (!out_host && b->num_digests)) return fail(ENG_ERR_INVALID, "NULL argument");
+    if (b->num_digests == 0) return ENG_OK;
+    return d2h(out_host, b->digests, (size_t)b->num_digests * 32);
+}
+
+eng_status eng_batch_coeffs(const eng_batch *b, uint32_t poly, uint64_t *out_host) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!b || !out_host) return fail(ENG_ERR_INVALID, "NULL argument");
+    if (!b->coeffs || poly >= b->num_polys) return fail(ENG_ERR_INVALID, "polynomial index %u out of range (%u)", poly, b->num_polys);
+    size_t n = (size_t)1 << b->degree_log;
+    return d2h(out_host, b->coeffs + (size_t)poly * n, n * 8);
+}
+
+static eng_status gather_rows(const eng_batch *b, uint64_t first, uint64_t count, uint32_t width, uint64_t *out_host) {
+    if (count == 0 || width == 0) return ENG_OK;
+    u64 *tmp;
+    ST(dev_alloc(&tmp, (size_t)count * width));
+    u64 total = count * width;
+    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g.stream>>>(b->leaf_data, b->row_stride, b->col_stride, width, first, count, tmp);
+    g.launches++;
+    cudaError_t e = cudaGetLastError();
+    eng_status s = e == cudaSuccess ? d2h(out_host, tmp, (size_t)total * 8) : fail(ENG_ERR_CUDA, "gather_rows_kernel: %s", cudaGetErrorString(e));
+    dev_free(tmp);
+    return s;
+}
+
+eng_status eng_batch_leaves(const eng_batch *b, uint64_t first, uint64_t count, uint64_t *out_host) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!b || (!out_host && count)) return fail(ENG_ERR_INVALID, "NULL argument");
+    if (first > b->num_leaves || count > b->num_leaves - first) return fail(ENG_ERR_INVALID, "leaf range [%llu, +%llu) out of bounds", (unsigned long long)first, (unsigned long long)count);
+    return gather_rows(b, first, count, b->leaf_len, out_host);
+}
+
+eng_status eng_batch_lde_values(const eng_batch *b, uint64_t index, uint64_t step, uint64_t *out_host) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!b || !out_host) return fail(ENG_ERR_INVALID, "NULL argument");
+    u32 bits = b->degree_log + b->rate_bits;
+    u64 i = index * step;
+    if (i >= b->num_leaves) return fail(ENG_ERR_INVALID, "index*step = %llu out of bounds", (unsigned long long)i);
+    u64 r = 0;
+    for (u32 k = 0; k < bits; k++) r |= ((i >> k) & 1) << (bits - 1 - k);
+    return gather_rows(b, r, 1, b->num_polys, out_host);
+}
+
+eng_status eng_batch_merkle_path(const eng_batch *b, uint64_t leaf_index, uint64_t *siblings_host, uint32_t *num_siblings) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!b || !num_siblings) return fail(ENG_ERR_INVALID, "NULL argument");
+    if (leaf_index >= b->num_leaves) return fail(ENG_ERR_INVALID, "leaf index %llu out of bounds", (unsigned long long)leaf_index);
+    *num_siblings = b->num_layers;
+    if (b->num_layers == 0) return ENG_OK;
+    if (!siblings_host) return fail(ENG_ERR_INVALID, "siblings_host is NULL");
+    // sibling of node g at layer i is node g^1 of the same layer
+    u64 g_idx = leaf_index;
+    for (u32 i = 0; i < b->num_layers; i++) {
+        u64 pos = merkle_digest_pos(b->num_layers, i, g_idx ^ 1);
+        CU(cudaMemcpyAsync(siblings_host + 4 * i, b->digests + 4 * pos, 32, cudaMemcpyDeviceToHost, g.stream));
+        g_idx >>= 1;
+    }
+    CU(cudaStreamSynchronize(g.stream));
+    return ENG_OK;
+}
+
+eng_status eng_batch_device_ptrs(const eng_batch *b, const uint64_t **lde_dev, const uint64_t **coeffs_dev,
+                                 const uint64_t **digests_dev, const uint64_t **cap_dev) {
+    if (!b) return fail(ENG_ERR_INVALID, "NULL argument");
+    if (lde_dev) *lde_dev = b->leaf_data;
+    if (coeffs_dev) *coeffs_dev = b->coeffs;
+    if (digests_dev) *digests_dev = b->digests;
+    if (cap_dev) *cap_dev = b->cap;
+    return ENG_OK;
+}
+
+eng_status eng_batch_stage_ms(const eng_batch *b, float out[6]) {
+    if (!b || !out) return fail(ENG_ERR_INVALID, "NULL argument");
+    memcpy(out, b->stage_ms, sizeof(b->stage_ms));
+    return ENG_OK;
+}
+
+}  // extern "C"

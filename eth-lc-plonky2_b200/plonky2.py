@@ -1,0 +1,239 @@
+"""Host-side mirror of the plonky2 operator surface that the engine replaces.
+
+Names, argument meaning and failure behaviour follow plonky2 0.1.4 (dep pinned at
+/root/reference/Cargo.lock:2347-2350; the reference reaches these through builder.build() and data.prove(),
+/root/reference/eth-lc-plonky2/src/main.rs:227,230):
+
+    PolynomialBatch::from_values / from_coeffs / get_lde_values      [plonky2:fri/oracle.rs]
+    MerkleTree::new / cap / get / prove, digests layout              [plonky2:hash/merkle_tree.rs]
+    PoseidonHash::hash_no_pad / hash_or_noop / two_to_one, poseidon  [plonky2:hash/poseidon.rs, hashing.rs]
+
+Everything is computed by the CUDA engine through the C ABI (include/plonky2_b200.h); batches stay resident
+on the device behind handles and the accessors below are gathers.  A violated plonky2 precondition (an
+assert!/expect panic in Rust) raises EngineError with status ENG_ERR_INVALID.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineError, check, host_u64, ptr
+
+SALT_SIZE = 4
+P = 0xFFFFFFFF00000001
+
+
+def _is_device_tensor(x):
+    return hasattr(x, "is_cuda") and x.is_cuda
+
+
+def poseidon(states):
+    """Poseidon::poseidon on one state (12,) or many (k, 12)."""
+    s = host_u64(states)
+    single = s.ndim == 1
+    s = s.reshape(-1, 12)
+    out = np.empty_like(s)
+    check(_lib.lib().eng_poseidon_permute(ptr(s), ptr(out), s.shape[0]))
+    return out[0] if single else out
+
+
+class PoseidonHash:
+    """plonky2::hash::poseidon::PoseidonHash (Hasher for PoseidonGoldilocksConfig)."""
+
+    @staticmethod
+    def _hash(inputs, or_noop):
+        a = host_u64(inputs)
+        single = a.ndim == 1
+        a = a.reshape(1, -1) if single else a
+        out = np.empty((a.shape[0], 4), np.uint64)
+        check(_lib.lib().eng_hash_n(ptr(a), a.shape[1], a.shape[0], int(or_noop), ptr(out)))
+        return out[0] if single else out
+
+    @staticmethod
+    def hash_no_pad(inputs):
+        return PoseidonHash._hash(inputs, False)
+
+    @staticmethod
+    def hash_or_noop(inputs):
+        return PoseidonHash._hash(inputs, True)
+
+    @staticmethod
+    def two_to_one(left, right):
+        l, r = host_u64(left).reshape(-1, 4), host_u64(right).reshape(-1, 4)
+        pairs = np.ascontiguousarray(np.concatenate([l, r], axis=1))
+        out = np.empty((pairs.shape[0], 4), np.uint64)
+        check(_lib.lib().eng_two_to_one(ptr(pairs), pairs.shape[0], ptr(out)))
+        return out[0] if np.ndim(left) == 1 else out
+
+
+class _Handle:
+    """Owner of an eng_batch* (Rust: Drop -> eng_batch_free)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        info = _lib.BatchInfo()
+        check(_lib.lib().eng_batch_info(self._h, C.byref(info)))
+        self.info = info
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().eng_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MerkleTree:
+    """plonky2::hash::merkle_tree::MerkleTree<F, PoseidonHash>."""
+
+    def __init__(self, handle_owner):
+        self._o = handle_owner
+
+    @classmethod
+    def new(cls, leaves, cap_height):
+        """MerkleTree::new(leaves: Vec<Vec<F>>, cap_height).  `leaves` is [num_leaves][leaf_len] (numpy, host)."""
+        a = host_u64(leaves)
+        if a.ndim != 2:
+            raise EngineError(_lib.ENG_ERR_INVALID, "leaves must be [num_leaves][leaf_len]")
+        h = C.c_void_p()
+        check(_lib.lib().eng_merkle_new(ptr(a), a.shape[0], a.shape[1], cap_height, C.byref(h)))
+        return cls(_Handle(h))
+
+    @property
+    def cap_height(self):
+        return self._o.info.cap_height
+
+    @property
+    def num_leaves(self):
+        return self._o.info.num_leaves
+
+    @property
+    def cap(self):
+        """MerkleCap: [2^cap_height][4]."""
+        out = np.empty((1 << self._o.info.cap_height, 4), np.uint64)
+        check(_lib.lib().eng_batch_cap(self._o._h, ptr(out)))
+        return out
+
+    @property
+    def digests(self):
+        """The `digests` vector in plonky2's interleaved order: [2*(L - 2^h)][4]."""
+        out = np.empty((self._o.info.num_digests, 4), np.uint64)
+        check(_lib.lib().eng_batch_digests(self._o._h, ptr(out)))
+        return out
+
+    def get(self, i):
+        """MerkleTree::get(i) -> &leaves[i]."""
+        return self.leaves(i, 1)[0]
+
+    def leaves(self, first=0, count=None):
+        """leaves[first : first+count], row-major."""
+        if count is None:
+            count = self._o.info.num_leaves - first
+        out = np.empty((count, self._o.info.leaf_len), np.uint64)
+        check(_lib.lib().eng_batch_leaves(self._o._h, first, count, ptr(out)))
+        return out
+
+    def prove(self, leaf_index):
+        """MerkleTree::prove(leaf_index).siblings, bottom-up: [log2(L) - cap_height][4]."""
+        n = C.c_uint32(0)
+        out = np.empty((64, 4), np.uint64)
+        check(_lib.lib().eng_batch_merkle_path(self._o._h, leaf_index, ptr(out), C.byref(n)))
+        return out[: n.value].copy()
+
+
+class PolynomialBatch:
+    """plonky2::fri::oracle::PolynomialBatch<F, C, D> resident on the device."""
+
+    def __init__(self, handle_owner):
+        self._o = handle_owner
+        self.merkle_tree = MerkleTree(handle_owner)
+
+    @staticmethod
+    def _make(data, rate_bits, blinding, cap_height, is_values, blinding_seed):
+        lib = _lib.lib()
+        h = C.c_void_p()
+        if _is_device_tensor(data):
+            if data.dim() != 2 or data.element_size() != 8 or not data.is_contiguous():
+                raise EngineError(_lib.ENG_ERR_INVALID, "device input must be a contiguous [num_polys][n] 64-bit tensor")
+            num_polys, n = data.shape
+            fn = lib.eng_batch_from_values_dev if is_values else lib.eng_batch_from_coeffs_dev
+            arg = C.c_void_p(data.data_ptr())
+            keep = None
+        else:
+            cols = [host_u64(c) for c in data]
+            if not cols:
+                raise EngineError(_lib.ENG_ERR_INVALID, "PolynomialBatch needs at least one polynomial")
+            n = cols[0].shape[0]
+            if any(c.ndim != 1 or c.shape[0] != n for c in cols):
+                # plonky2: "All polynomials must have the same length"
+                raise EngineError(_lib.ENG_ERR_INVALID, "all polynomials must have the same length")
+            num_polys = len(cols)
+            fn = lib.eng_batch_from_values if is_values else lib.eng_batch_from_coeffs
+            keep = (C.c_void_p * num_polys)(*[c.ctypes.data for c in cols])
+            arg = keep
+        if n == 0 or n & (n - 1):
+            raise EngineError(_lib.ENG_ERR_INVALID, "polynomial length %d is not a power of two (log2_strict)" % n)
+        log_n = n.bit_length() - 1
+        check(fn(arg, num_polys, log_n, rate_bits, int(bool(blinding)), blinding_seed, cap_height, C.byref(h)))
+        return PolynomialBatch(_Handle(h))
+
+    @classmethod
+    def from_values(cls, values, rate_bits, blinding, cap_height, timing=None, fft_root_table=None, blinding_seed=0):
+        """PolynomialBatch::from_values(values: Vec<PolynomialValues<F>>, rate_bits, blinding, cap_height, ..)."""
+        return cls._make(values, rate_bits, blinding, cap_height, True, blinding_seed)
+
+    @classmethod
+    def from_coeffs(cls, polynomials, rate_bits, blinding, cap_height, timing=None, fft_root_table=None, blinding_seed=0):
+        """PolynomialBatch::from_coeffs(polynomials: Vec<PolynomialCoeffs<F>>, rate_bits, blinding, cap_height, ..)."""
+        return cls._make(polynomials, rate_bits, blinding, cap_height, False, blinding_seed)
+
+    # ---- fields ----
+    @property
+    def degree_log(self):
+        return self._o.info.degree_log
+
+    @property
+    def rate_bits(self):
+        return self._o.info.rate_bits
+
+    @property
+    def blinding(self):
+        return bool(self._o.info.blinding)
+
+    @property
+    def num_polys(self):
+        return self._o.info.num_polys
+
+    @property
+    def polynomials(self):
+        """Vec<PolynomialCoeffs<F>> as [num_polys][n] (device -> host copy)."""
+        n = 1 << self._o.info.degree_log
+        out = np.empty((self._o.info.num_polys, n), np.uint64)
+        for c in range(self._o.info.num_polys):
+            check(_lib.lib().eng_batch_coeffs(self._o._h, c, ptr(out[c])))
+        return out
+
+    def get_lde_values(self, index, step):
+        """leaves[bitrev(index*step)] without the salt."""
+        out = np.empty(self._o.info.num_polys, np.uint64)
+        check(_lib.lib().eng_batch_lde_values(self._o._h, index, step, ptr(out)))
+        return out
+
+    def stage_ms(self):
+        """Device time per stage, keyed by plonky2's timed! labels."""
+        t = (C.c_float * 6)()
+        check(_lib.lib().eng_batch_stage_ms(self._o._h, t))
+        return {"IFFT": t[0], "FFT + blinding": t[1], "transpose LDEs": t[2], "build Merkle tree (leaves)": t[3],
+                "build Merkle tree (digest levels)": t[4], "host to device": t[5]}
+
+    def device_ptrs(self):
+        p = [C.c_void_p() for _ in range(4)]
+        check(_lib.lib().eng_batch_device_ptrs(self._o._h, *[C.byref(x) for x in p]))
+        return {"lde": p[0].value, "coeffs": p[1].value, "digests": p[2].value, "cap": p[3].value}
+
+    def close(self):
+        self._o.close()

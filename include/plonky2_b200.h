@@ -1,0 +1,123 @@
+/* plonky2_b200.h -- C ABI of the B200-native plonky2 commitment engine (libplonky2_b200.so).
+ *
+ * Drop-in boundary for the hot path of Electron-Labs/eth-lc-plonky2: the operators of the un-vendored
+ * dependency plonky2 0.1.4 (git 666f3151..., pinned at /root/reference/Cargo.lock:2347-2350) that
+ * `builder.build::<C>()` and `data.prove(witness)` spend their time in
+ * (/root/reference/eth-lc-plonky2/src/main.rs:227 and :230; every test goes through
+ * /root/reference/eth-lc-plonky2/src/unit_tests.rs:29-35).  plonky2 has no plugin trait for them; the seam is a
+ * Cargo [patch] of the git dependency (/root/reference/Cargo.toml:21-23,
+ * /root/reference/eth-lc-plonky2/Cargo.toml:9) whose operator bodies call these symbols -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - Field elements are little-endian uint64_t (GoldilocksField is #[repr(transparent)] over u64); inputs may be
+ *     non-canonical, every output is the canonical representative (< p = 2^64 - 2^32 + 1).
+ *   - Digests (HashOut<F>) are 4 x uint64_t.
+ *   - Every function returns an eng_status; it never unwinds.  On failure eng_last_error() gives the message that
+ *     the Rust shim turns into the panic!/anyhow! plonky2 would have raised
+ *     (the four #[should_panic] tests, /root/reference/eth-lc-plonky2/src/unit_tests.rs:377,555,654,686).
+ *   - Pointers named *_host are host memory owned by the caller for the duration of the call; *_dev are device
+ *     pointers on the engine's device.  Batches are device-resident behind opaque handles (Rust: Drop ->
+ *     eng_batch_free).  The API is re-entrant (one internal lock; `cargo test` runs proofs on parallel threads).
+ *   - There is no CPU path: without a CUDA device eng_init fails and every other call returns ENG_ERR_STATE.
+ */
+#ifndef PLONKY2_B200_H
+#define PLONKY2_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t eng_status;
+#define ENG_OK 0
+#define ENG_ERR_INVALID 1 /* a plonky2 assert!/expect would have fired (bad sizes, cap_height > log2(leaves), ...) */
+#define ENG_ERR_CUDA 2    /* CUDA runtime error (sticky errors are reported on every later call) */
+#define ENG_ERR_OOM 3     /* device allocation failed */
+#define ENG_ERR_STATE 4   /* engine not initialised / no device */
+
+typedef struct eng_batch eng_batch; /* PolynomialBatch (or a bare MerkleTree) resident on the device */
+
+/* ---- lifecycle ---- */
+eng_status eng_init(int32_t device);             /* idempotent; device = CUDA ordinal (one process per GPU) */
+eng_status eng_shutdown(void);
+eng_status eng_last_error(char *buf, size_t len); /* message of the calling thread's last failure */
+eng_status eng_set_stream(void *cuda_stream);     /* run on the caller's cudaStream_t (NULL = engine's own) */
+eng_status eng_synchronize(void);
+eng_status eng_launch_count(uint64_t *out);       /* kernels launched by the engine since eng_init */
+
+/* Measured integer issue rates of this device, thread-operations per second:
+ * [0] 32-bit IMAD (mad.lo.u32)  [1] IMAD.WIDE (mad.wide.u32)  [2] alu-pipe ops (add/xor).  The roofline denominators
+ * for the Poseidon kernels (MEASURED_PEAKS.json only has HBM and bf16). */
+eng_status eng_measure_int_peak(double ops_per_s[3]);
+
+/* ---- a4: PoseidonHash / Poseidon::poseidon  [plonky2:hash/poseidon.rs, hash/hashing.rs] ---- */
+/* Poseidon::poseidon on `count` states of 12 lanes. */
+eng_status eng_poseidon_permute(const uint64_t *states_host, uint64_t *out_host, size_t count);
+/* PoseidonHash::hash_no_pad (or_noop = 0) / hash_or_noop (or_noop = 1) of `count` inputs of `len` elements each. */
+eng_status eng_hash_n(const uint64_t *in_host, size_t len, size_t count, int32_t or_noop, uint64_t *out_host);
+/* PoseidonHash::two_to_one on `count` pairs [l(4) | r(4)]. */
+eng_status eng_two_to_one(const uint64_t *pairs_host, size_t count, uint64_t *out_host);
+
+/* ---- a1/a2: PolynomialBatch::from_values / from_coeffs  [plonky2:fri/oracle.rs] ----
+ * cols_host[c] points at polynomial c (2^log_n elements).  blinding != 0 appends SALT_SIZE = 4 random leaf
+ * elements per row (plonky2 draws them from OsRng; here a SplitMix64 stream seeded with blinding_seed).
+ * timing / fft_root_table of the Rust signature have no counterpart: stage times are read back with
+ * eng_batch_stage_ms, root tables are cached inside the engine. */
+eng_status eng_batch_from_values(const uint64_t *const *cols_host, uint32_t num_polys, uint32_t log_n,
+                                 uint32_t rate_bits, int32_t blinding, uint64_t blinding_seed, uint32_t cap_height,
+                                 eng_batch **out);
+eng_status eng_batch_from_coeffs(const uint64_t *const *cols_host, uint32_t num_polys, uint32_t log_n,
+                                 uint32_t rate_bits, int32_t blinding, uint64_t blinding_seed, uint32_t cap_height,
+                                 eng_batch **out);
+/* Same, input already on the device as [num_polys][2^log_n] (column-major, contiguous). */
+eng_status eng_batch_from_values_dev(const uint64_t *values_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits,
+                                     int32_t blinding, uint64_t blinding_seed, uint32_t cap_height, eng_batch **out);
+eng_status eng_batch_from_coeffs_dev(const uint64_t *coeffs_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits,
+                                     int32_t blinding, uint64_t blinding_seed, uint32_t cap_height, eng_batch **out);
+eng_status eng_batch_free(eng_batch *b);
+
+/* ---- a3: MerkleTree::new(leaves, cap_height)  [plonky2:hash/merkle_tree.rs] ----
+ * leaves_host is row-major [num_leaves][leaf_len].  ENG_ERR_INVALID when cap_height > log2(num_leaves) or
+ * num_leaves is not a power of two (plonky2 panics). */
+eng_status eng_merkle_new(const uint64_t *leaves_host, uint64_t num_leaves, uint32_t leaf_len, uint32_t cap_height,
+                          eng_batch **out);
+/* Leaves already on the device: element (row, col) at data_dev[row*row_stride + col*col_stride]; not copied, the
+ * caller keeps data_dev alive for the life of the handle. */
+eng_status eng_merkle_new_dev(const uint64_t *data_dev, uint64_t row_stride, uint64_t col_stride, uint64_t num_leaves,
+                              uint32_t leaf_len, uint32_t cap_height, eng_batch **out);
+
+/* ---- accessors (PolynomialBatch fields, MerkleTree::{cap, get, prove}, get_lde_values) ---- */
+typedef struct {
+    uint32_t num_polys;   /* polynomials.len() (0 for a bare MerkleTree) */
+    uint32_t degree_log;  /* PolynomialBatch::degree_log */
+    uint32_t rate_bits;
+    uint32_t cap_height;
+    uint32_t blinding;
+    uint32_t leaf_len;    /* num_polys (+4 salt) or MerkleTree leaf length */
+    uint64_t num_leaves;  /* 2^(degree_log + rate_bits) */
+    uint64_t num_digests; /* 2 * (num_leaves - 2^cap_height) */
+} eng_batch_info_t;
+eng_status eng_batch_info(const eng_batch *b, eng_batch_info_t *out);
+eng_status eng_batch_cap(const eng_batch *b, uint64_t *out_host);                    /* [2^cap_height][4] */
+eng_status eng_batch_digests(const eng_batch *b, uint64_t *out_host);                /* plonky2's `digests` order */
+eng_status eng_batch_coeffs(const eng_batch *b, uint32_t poly, uint64_t *out_host);  /* polynomials[poly].coeffs */
+/* merkle_tree.leaves[first .. first+count], row-major [count][leaf_len] */
+eng_status eng_batch_leaves(const eng_batch *b, uint64_t first, uint64_t count, uint64_t *out_host);
+/* get_lde_values(index, step) = leaves[bitrev(index*step)] without the salt: num_polys elements */
+eng_status eng_batch_lde_values(const eng_batch *b, uint64_t index, uint64_t step, uint64_t *out_host);
+/* merkle_tree.prove(leaf_index).siblings, bottom-up; *num_siblings = log2(num_leaves) - cap_height */
+eng_status eng_batch_merkle_path(const eng_batch *b, uint64_t leaf_index, uint64_t *siblings_host, uint32_t *num_siblings);
+/* Device views for device-side consumers (quotient, FRI): lde is [leaf_len][num_leaves] column-major in
+ * bit-reversed row order; coeffs is [num_polys][2^degree_log]. */
+eng_status eng_batch_device_ptrs(const eng_batch *b, const uint64_t **lde_dev, const uint64_t **coeffs_dev,
+                                 const uint64_t **digests_dev, const uint64_t **cap_dev);
+/* Stage times of the call that built the batch, ms, in the order of plonky2's timed! labels:
+ * [0] "IFFT"  [1] "FFT + blinding"  [2] "transpose LDEs" (always 0: the layout makes it implicit)
+ * [3] "build Merkle tree" leaf hashing  [4] "build Merkle tree" digest levels + cap  [5] host->device copies */
+eng_status eng_batch_stage_ms(const eng_batch *b, float out[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,116 @@
+// CPU replay of the CUDA kernels -- TEST HARNESS ONLY (never shipped, never loaded by the product package).
+//
+// The development container has no GPU, so this file compiles the kernel BODIES of
+// eth-lc-plonky2_b200/csrc/{ntt,merkle,poseidon}.cuh (written as __host__ __device__ functions) with g++ and
+// replays every launch of a plan block by block, thread by thread, phase by phase (each __syncthreads()
+// boundary is a loop boundary).  It checks the index math, table construction and planner on the CPU against
+// the oracle before GPU minutes are spent; the `-m gpu` tests then check the real kernels through the C ABI.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+#include "../../eth-lc-plonky2_b200/csrc/merkle.cuh"
+#include "../../eth-lc-plonky2_b200/csrc/ntt.cuh"
+#include "../../eth-lc-plonky2_b200/csrc/ntt_plan.h"
+
+static std::vector<std::unique_ptr<std::vector<u64>>> g_tables;
+
+static NttTableStore make_store() {
+    NttTableStore ts;
+    ts.upload = [](const std::vector<u64> &t) -> const u64 * {
+        g_tables.emplace_back(new std::vector<u64>(t));
+        return g_tables.back()->data();
+    };
+    return ts;
+}
+
+template <int MODE>
+static void replay_mode(const NttLaunch &l, u64 grid) {
+    std::vector<u64> sm(l.smem / 8 + 16);
+    const NttPass &p = l.p;
+    for (u64 bid = 0; bid < grid; bid++) {
+        for (u64 tile = bid; tile < p.num_tiles; tile += grid) {
+            for (u32 t = 0; t < l.threads; t++) ntt_load<MODE>(p, sm.data(), tile, t, l.threads);
+            u32 t0 = 0, rem = p.log_p & 3;
+            if (rem == 1) { for (u32 t = 0; t < l.threads; t++) ntt_round<1>(p, sm.data(), t0, t, l.threads); t0 += 1; }
+            if (rem == 2) { for (u32 t = 0; t < l.threads; t++) ntt_round<2>(p, sm.data(), t0, t, l.threads); t0 += 2; }
+            if (rem == 3) { for (u32 t = 0; t < l.threads; t++) ntt_round<3>(p, sm.data(), t0, t, l.threads); t0 += 3; }
+            for (; t0 < p.log_p; t0 += 4)
+                for (u32 t = 0; t < l.threads; t++) ntt_round<4>(p, sm.data(), t0, t, l.threads);
+            for (u32 t = 0; t < l.threads; t++) ntt_store<MODE>(p, sm.data(), tile, t, l.threads);
+        }
+    }
+}
+static void replay(const std::vector<NttLaunch> &plan, u64 grid) {
+    for (const NttLaunch &l : plan) {
+        switch (l.mode) {
+            case NTT_LDE_FIRST: replay_mode<NTT_LDE_FIRST>(l, grid); break;
+            case NTT_LDE_SINGLE: replay_mode<NTT_LDE_SINGLE>(l, grid); break;
+            case NTT_DIF_LAST: replay_mode<NTT_DIF_LAST>(l, grid); break;
+            case NTT_INTT_P1: replay_mode<NTT_INTT_P1>(l, grid); break;
+            case NTT_INTT_P2: replay_mode<NTT_INTT_P2>(l, grid); break;
+            case NTT_INTT_SINGLE: replay_mode<NTT_INTT_SINGLE>(l, grid); break;
+            default: abort();
+        }
+    }
+}
+
+extern "C" {
+
+void emu_poseidon_permute(const u64 *in, u64 *out, size_t count) {
+    for (size_t i = 0; i < count; i++) {
+        u64 s[12];
+        for (int k = 0; k < 12; k++) s[k] = in[12 * i + k];
+        poseidon_permute(s);
+        for (int k = 0; k < 12; k++) out[12 * i + k] = gl_canon(s[k]);
+    }
+}
+
+u64 emu_gl_mul(u64 a, u64 b) { return gl_canon(gl_mul(a, b)); }
+u64 emu_gl_add(u64 a, u64 b) { return gl_canon(gl_add(a, b)); }
+u64 emu_gl_sub(u64 a, u64 b) { return gl_canon(gl_sub(a, b)); }
+
+// values [C][n] -> coeffs [C][n], lde [C][L] (column-major, bit-reversed rows), digests, cap.  Returns 0 on success.
+int emu_batch_from_values(const u64 *values, u32 C, u32 log_n, u32 rate_bits, u32 cap_height, int is_values, u64 grid,
+                          u64 *coeffs, u64 *lde, u64 *digests, u64 *cap) {
+    NttTableStore ts = make_store();
+    const u64 n = (u64)1 << log_n, L = n << rate_bits;
+    std::vector<NttLaunch> plan;
+    if (is_values) {
+        if (!ntt_plan_intt(ts, values, n, lde, n, coeffs, n, C, log_n, plan)) return 1;
+        replay(plan, grid);
+    } else {
+        memcpy(coeffs, values, (size_t)C * n * 8);
+    }
+    plan.clear();
+    if (!ntt_plan_lde(ts, coeffs, n, lde, L, C, log_n, rate_bits, plan)) return 2;
+    replay(plan, grid);
+    MerkleParams mp;
+    mp.data = lde; mp.row_stride = 1; mp.col_stride = L; mp.width = C; mp.noop_max = 4; mp.num_leaves = L;
+    mp.num_layers = log_n + rate_bits - cap_height; mp.digests = digests; mp.cap = cap;
+    for (u64 j = 0; j < L; j++) merkle_hash_leaf(mp, j);
+    for (u32 layer = 0; layer < mp.num_layers; layer++)
+        for (u64 gidx = 0; gidx < (L >> (layer + 1)); gidx++) merkle_hash_node(mp, layer, gidx);
+    g_tables.clear();
+    return 0;
+}
+
+// describes the launch list (for tests of the planner): fills up to max entries of [mode, log_p, log_a, threads, smem, tiles]
+int emu_plan(u32 C, u32 log_n, u32 rate_bits, int intt, u64 *out, int max) {
+    NttTableStore ts = make_store();
+    std::vector<NttLaunch> plan;
+    std::vector<u64> dummy(1);
+    bool ok = intt ? ntt_plan_intt(ts, dummy.data(), 0, dummy.data(), 0, dummy.data(), 0, C, log_n, plan)
+                   : ntt_plan_lde(ts, dummy.data(), 0, dummy.data(), 0, C, log_n, rate_bits, plan);
+    g_tables.clear();
+    if (!ok) return -1;
+    int k = 0;
+    for (const NttLaunch &l : plan) {
+        if (k >= max) break;
+        u64 *o = out + 6 * k++;
+        o[0] = l.mode; o[1] = l.p.log_p; o[2] = l.p.log_a; o[3] = l.threads; o[4] = l.smem; o[5] = l.p.num_tiles;
+    }
+    return k;
+}
+}

@@ -1,0 +1,209 @@
+"""Parity of the CUDA engine (through the C ABI) with the CPU oracle and the golden vectors.  Bit-exact: all work
+is integer arithmetic mod p = 2^64 - 2^32 + 1, compared on canonical representatives."""
+import numpy as np
+import pytest
+
+from helpers import P, bitrev, golden, hx, poly_eval, rand_field, sha, structured, unhx
+
+pytestmark = pytest.mark.gpu
+
+
+def test_poseidon_upstream_kats(engine):
+    for inp, want in golden()["poseidon_kats"]:
+        assert hx(engine.poseidon(unhx(inp))) == want
+
+
+def test_poseidon_random_vs_oracle(engine, oracle):
+    rng = np.random.default_rng(2)
+    st = rand_field(rng, (4096, 12), noncanonical=True)
+    st[0] = 2**64 - 1; st[1] = P; st[2] = P - 1
+    out = engine.poseidon(st)
+    for i in list(range(16)) + list(range(16, 4096, 97)):
+        assert (oracle.poseidon(st[i]) == out[i]).all()
+
+
+def test_sponge_vectors(engine, oracle):
+    g = golden()["sponge"]
+    H = engine.PoseidonHash
+    assert hx(H.hash_no_pad([1, 2, 3])) == g["hash_no_pad_1_2_3"]
+    assert hx(H.hash_no_pad(np.arange(135))) == g["hash_no_pad_0_to_134"]
+    h = H.hash_no_pad([1, 2, 3])
+    assert hx(H.two_to_one(h, h)) == g["two_to_one_h_h"]
+    assert hx(H.hash_or_noop([5, 6, 7])) == hx([5, 6, 7, 0])
+    assert hx(H.hash_or_noop([P + 5, 6, 7, 2**64 - 1])) == hx([5, 6, 7, 2**64 - 1 - P])   # canonical on the way out
+    rng = np.random.default_rng(4)
+    for ln in (1, 4, 5, 8, 9, 16, 17, 135, 139):
+        a = rand_field(rng, (33, ln), noncanonical=True)
+        got_np, got_on = H.hash_no_pad(a), H.hash_or_noop(a)
+        for i in (0, 16, 32):
+            assert (got_np[i] == oracle.hash_no_pad(a[i])).all()
+            assert (got_on[i] == oracle.hash_or_noop(a[i])).all()
+
+
+def _check_batch(engine, oracle, vals, r, h, is_values=True, full=True):
+    PB = engine.PolynomialBatch
+    b = PB.from_values(list(vals), r, False, h) if is_values else PB.from_coeffs(list(vals), r, False, h)
+    o = oracle.Batch.from_values(vals, r, h) if is_values else oracle.Batch.from_coeffs(vals, r, h)
+    assert b.degree_log == o.log_n and b.rate_bits == r and not b.blinding
+    assert (b.polynomials == o.coeffs).all()
+    assert (b.merkle_tree.cap == o.cap).all()
+    if full:
+        assert (b.merkle_tree.leaves() == o.leaves).all()
+        assert (b.merkle_tree.digests == o.digests).all()
+    L = o.L
+    for k in sorted({0, 1, L - 1, L // 2, (L * 5) // 7}):
+        assert (b.merkle_tree.get(k) == o.leaves[k]).all()
+        assert (b.merkle_tree.prove(k) == o.prove(k)).all()
+    b.close()
+    return o
+
+
+@pytest.mark.parametrize("C_,log_n,r,h", [(3, 0, 1, 0), (3, 1, 1, 1), (5, 2, 2, 0), (9, 3, 1, 1), (3, 3, 3, 2), (135, 4, 3, 4),
+                                          (7, 5, 3, 2), (9, 7, 2, 3), (2, 10, 1, 4), (3, 12, 3, 4), (9, 12, 0, 0), (3, 13, 1, 4),
+                                          (2, 13, 3, 0), (5, 14, 2, 4), (2, 15, 3, 4), (135, 12, 3, 4), (20, 16, 3, 4),
+                                          (16, 17, 3, 4), (4, 18, 2, 4), (2, 20, 1, 4)])
+def test_from_values_matches_oracle(engine, oracle, C_, log_n, r, h):
+    rng = np.random.default_rng(1000 * C_ + log_n)
+    vals = rand_field(rng, (C_, 1 << log_n), noncanonical=True)
+    _check_batch(engine, oracle, vals, r, h)
+
+
+@pytest.mark.parametrize("C_,log_n,r,h", [(16, 3, 3, 4), (16, 13, 3, 4), (4, 9, 4, 4), (2, 14, 4, 1)])
+def test_from_coeffs_matches_oracle(engine, oracle, C_, log_n, r, h):
+    rng = np.random.default_rng(77 * C_ + log_n)
+    vals = rand_field(rng, (C_, 1 << log_n), noncanonical=True)
+    _check_batch(engine, oracle, vals, r, h, is_values=False)
+
+
+def test_golden_structured_commits(engine):
+    for c in golden()["commits_structured"]:
+        b = engine.PolynomialBatch.from_values(list(structured(c["C"], c["n"])), c["rate_bits"], False, c["cap_height"])
+        t = b.merkle_tree
+        assert hx(b.polynomials[1][:3]) == c["coeffs_1_0_3"]
+        assert hx(t.get(1)[:3]) == c["leaf_1_0_3"]
+        assert hx(t.digests[0]) == c["digests_0"]
+        assert hx(t.cap[0]) == c["cap_0"] and hx(t.cap[-1]) == c["cap_last"]
+        assert sha(t.cap) == c["sha256_cap"] and sha(t.leaves()) == c["sha256_leaves"]
+
+
+def test_golden_generated_commits(engine, oracle):
+    for g in golden()["oracle_generated"]:
+        vals = oracle.splitmix_columns(g["C"], 1 << g["log_n"])
+        b = engine.PolynomialBatch.from_values(list(vals), g["rate_bits"], False, g["cap_height"])
+        assert sha(b.polynomials) == g["sha256_coeffs"]
+        assert sha(b.merkle_tree.leaves()) == g["sha256_leaves"]
+        assert sha(b.merkle_tree.digests) == g["sha256_digests"]
+        assert sha(b.merkle_tree.cap) == g["sha256_cap"] and hx(b.merkle_tree.cap[0]) == g["cap_0"]
+
+
+def test_device_input_equals_host_input(engine, oracle):
+    import torch
+    vals = oracle.splitmix_columns(20, 1 << 13)
+    a = engine.PolynomialBatch.from_values(list(vals), 3, False, 4)
+    t = torch.from_numpy(vals.view(np.int64)).cuda()
+    b = engine.PolynomialBatch.from_values(t, 3, False, 4)
+    assert (a.merkle_tree.cap == b.merkle_tree.cap).all() and (a.polynomials == b.polynomials).all()
+    assert (t.cpu().numpy().view(np.uint64) == vals).all()      # the caller's buffer is not modified
+
+
+def test_get_lde_values(engine, oracle):
+    rng = np.random.default_rng(9)
+    vals = rand_field(rng, (6, 1 << 6))
+    b = engine.PolynomialBatch.from_values(list(vals), 3, False, 2)
+    o = oracle.Batch.from_values(vals, 3, 2)
+    wl = oracle.lib().orc_root_of_unity(9)
+    for index, step in ((0, 1), (5, 1), (5, 8), (63, 8), (511, 1)):
+        row = b.get_lde_values(index, step)
+        assert (row == o.leaves[bitrev(index * step, 9)]).all()
+        x = 7 * pow(wl, index * step, P) % P                    # natural index i*step <-> point 7*w_L^(i*step)
+        assert int(row[2]) == poly_eval(o.coeffs[2], x)
+
+
+def test_merkle_tree_new_rowmajor(engine, oracle):
+    rng = np.random.default_rng(21)
+    for L, w, h in ((1, 3, 0), (2, 9, 1), (8, 5, 3), (64, 32, 4), (1 << 12, 32, 4), (1 << 10, 4, 2), (256, 1, 0), (1 << 11, 135, 4)):
+        leaves = rand_field(rng, (L, w), noncanonical=True)
+        t = engine.MerkleTree.new(leaves, h)
+        o = oracle.MerkleTree(leaves, h)
+        assert (t.cap == o.cap).all() and (t.digests == o.digests).all()
+        for k in sorted({0, L - 1, L // 3}):
+            assert (t.prove(k) == o.prove(k)).all()
+            assert oracle.merkle_verify(t.get(k), k, t.cap, t.prove(k))
+
+
+def test_preconditions_raise_like_plonky2_panics(engine):
+    E = engine
+    with pytest.raises(E.EngineError) as ei:
+        E.MerkleTree.new(np.zeros((8, 5), np.uint64), 4)                      # cap_height > log2(leaves)
+    assert ei.value.status == E.ENG_ERR_INVALID and "cap_height" in str(ei.value)
+    with pytest.raises(E.EngineError):
+        E.MerkleTree.new(np.zeros((6, 5), np.uint64), 1)                      # not a power of two
+    with pytest.raises(E.EngineError):
+        E.PolynomialBatch.from_values([np.zeros(8, np.uint64), np.zeros(4, np.uint64)], 3, False, 2)   # unequal lengths
+    with pytest.raises(E.EngineError):
+        E.PolynomialBatch.from_values([np.zeros(6, np.uint64)], 3, False, 2)  # not a power of two
+    with pytest.raises(E.EngineError):
+        E.PolynomialBatch.from_values([np.zeros(4, np.uint64)], 1, False, 4)  # cap_height > log2(L)
+    b = E.PolynomialBatch.from_values([np.arange(8, dtype=np.uint64)], 1, False, 1)
+    with pytest.raises(E.EngineError):
+        b.merkle_tree.prove(16)
+    with pytest.raises(E.EngineError):
+        b.merkle_tree.get(16)
+    # the engine is still usable after errors
+    assert b.merkle_tree.cap.shape == (2, 4)
+
+
+def test_blinding_appends_salt(engine, oracle):
+    rng = np.random.default_rng(5)
+    vals = rand_field(rng, (5, 1 << 5))
+    b = engine.PolynomialBatch.from_values(list(vals), 2, True, 1, blinding_seed=1234)
+    o = oracle.Batch.from_values(vals, 2, 1)
+    leaves = b.merkle_tree.leaves()
+    assert leaves.shape == (128, 5 + engine.SALT_SIZE) and b.blinding
+    assert (leaves[:, :5] == o.leaves).all() and (leaves[:, 5:] < np.uint64(P)).all()
+    assert len(np.unique(leaves[:, 5:])) > 500                 # salt is not constant
+    assert (b.get_lde_values(3, 1) == o.leaves[bitrev(3, 7)]).all()   # salt is stripped
+    t = oracle.MerkleTree(leaves, 1)                            # the tree commits to the salted rows
+    assert (t.cap == b.merkle_tree.cap).all()
+    b2 = engine.PolynomialBatch.from_values(list(vals), 2, True, 1, blinding_seed=1234)
+    assert (b2.merkle_tree.cap == b.merkle_tree.cap).all()     # seeded => reproducible
+
+
+def test_full_size_properties(engine, oracle):
+    """BASELINE config #2 shape (135 x 2^20, rate_bits 3, cap_height 4) through size-independent properties."""
+    import torch
+    C_, log_n, r, h = 135, 20, 3, 4
+    n, L = 1 << log_n, 1 << (log_n + r)
+    vals = oracle.splitmix_columns(C_, n)
+    t = torch.from_numpy(vals.view(np.int64)).cuda()
+    b = engine.PolynomialBatch.from_values(t, r, False, h)
+    tree = b.merkle_tree
+    cap = tree.cap
+    rng = np.random.default_rng(0)
+    wl, wn = oracle.lib().orc_root_of_unity(log_n + r), oracle.lib().orc_root_of_unity(log_n)
+    # (1) iNTT interpolates: column 0 and 134 evaluate back to the witness on the subgroup
+    for c in (0, 134):
+        co = b_poly = None
+        co = np.empty(n, np.uint64)
+        from eth_lc_plonky2_b200._lib import check, lib, ptr
+        check(lib().eng_batch_coeffs(b._o._h, c, ptr(co)))
+        assert (co < np.uint64(P)).all()
+        for i in (0, 1, n - 1, int(rng.integers(n))):
+            assert poly_eval(co, pow(wn, i, P)) == int(vals[c][i])
+        # (2) LDE row k holds f(7 w_L^bitrev(k)); (3) its Merkle path verifies against the cap
+        for k in (0, L - 1, int(rng.integers(L))):
+            row = tree.get(k)
+            assert int(row[c]) == poly_eval(co, 7 * pow(wl, bitrev(k, log_n + r), P) % P)
+            assert oracle.merkle_verify(row, k, cap, tree.prove(k))
+    # (4) cap is reproducible and depends on every column: changing one element changes it
+    t2 = t.clone(); t2[77, 12345] += 1
+    b2 = engine.PolynomialBatch.from_values(t2, r, False, h)
+    assert not (b2.merkle_tree.cap == cap).all()
+    b2.close()
+    b3 = engine.PolynomialBatch.from_values(t, r, False, h)
+    assert (b3.merkle_tree.cap == cap).all()
+    # (5) the oracle agrees on a sub-batch of full length (8 columns)
+    o = oracle.Batch.from_values(vals[:8], r, h)
+    b8 = engine.PolynomialBatch.from_values(t[:8].contiguous(), r, False, h)
+    assert (b8.merkle_tree.cap == o.cap).all()
+    assert sha(b8.merkle_tree.leaves(L - 4096, 4096)) == sha(o.leaves[L - 4096:])

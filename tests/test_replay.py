@@ -1,0 +1,90 @@
+"""CPU replay of the CUDA kernel bodies (tests/emu) against the oracle.
+
+The dev container has no GPU; tests/emu compiles the __host__ __device__ bodies of the kernels with g++ and replays
+each launch block by block / thread by thread.  This checks tile index maps, twiddle and shift tables, the pass
+planner and the Merkle digest layout before the `-m gpu` tests run the real kernels through the C ABI."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import P, rand_field
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(HERE, "emu", "libemu.so")
+    src = os.path.join(HERE, "emu", "emu.cpp")
+    csrc = os.path.join(HERE, "..", "eth-lc-plonky2_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    L = C.CDLL(so)
+    L.emu_poseidon_permute.argtypes = [u64p, u64p, C.c_size_t]
+    L.emu_batch_from_values.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, u64p, u64p, u64p, u64p]
+    L.emu_batch_from_values.restype = C.c_int
+    L.emu_plan.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u64p, C.c_int]
+    L.emu_plan.restype = C.c_int
+    for f in (L.emu_gl_mul, L.emu_gl_add, L.emu_gl_sub):
+        f.argtypes = [C.c_uint64, C.c_uint64]; f.restype = C.c_uint64
+    return L
+
+
+def test_field_ops_any_u64(emu):
+    rng = np.random.default_rng(5)
+    edge = [0, 1, P - 1, P, P + 1, 2**64 - 1, 2**32 - 1, 2**32, 2**64 - 2**32]
+    pairs = [(a, b) for a in edge for b in edge] + [tuple(int(v) for v in x) for x in rand_field(rng, (300, 2), noncanonical=True)]
+    for a, b in pairs:
+        assert emu.emu_gl_mul(a, b) == (a * b) % P
+        assert emu.emu_gl_add(a, b) == (a + b) % P
+        assert emu.emu_gl_sub(a, b) == (a - b) % P
+
+
+def test_poseidon_body(emu, oracle):
+    rng = np.random.default_rng(1)
+    st = rand_field(rng, (40, 12), noncanonical=True)
+    st[0] = 0; st[1] = np.arange(12); st[2] = P - 1; st[3] = 2**64 - 1
+    out = np.zeros_like(st)
+    emu.emu_poseidon_permute(st, out, st.shape[0])
+    for i in range(st.shape[0]):
+        assert (oracle.poseidon(st[i]) == out[i]).all()
+
+
+CASES = [(3, 0, 1, 0), (3, 1, 1, 1), (5, 2, 2, 0), (9, 3, 1, 1), (3, 3, 3, 2), (135, 4, 3, 4), (7, 5, 3, 2), (9, 7, 2, 3),
+         (2, 10, 1, 4), (3, 12, 2, 4), (3, 13, 1, 4), (2, 13, 3, 0), (3, 14, 2, 4)]
+
+
+@pytest.mark.parametrize("C_,log_n,r,h", CASES)
+@pytest.mark.parametrize("is_values", [1, 0])
+def test_commit_replay_matches_oracle(emu, oracle, C_, log_n, r, h, is_values):
+    if not is_values and log_n not in (3, 7, 13):
+        pytest.skip("from_coeffs replay on a subset")
+    rng = np.random.default_rng(1000 * C_ + log_n)
+    n = 1 << log_n; L = n << r
+    vals = rand_field(rng, (C_, n), noncanonical=True)
+    coeffs = np.zeros((C_, n), np.uint64); lde = np.zeros((C_, L), np.uint64)
+    nd = 2 * (L - (1 << h))
+    dig = np.zeros((max(nd, 1), 4), np.uint64); cap = np.zeros((1 << h, 4), np.uint64)
+    assert emu.emu_batch_from_values(vals, C_, log_n, r, h, is_values, 3, coeffs, lde, dig, cap) == 0
+    b = oracle.Batch.from_values(vals, r, h) if is_values else oracle.Batch.from_coeffs(vals, r, h)
+    assert (b.coeffs == coeffs).all()
+    assert (b.leaves == lde.T).all()          # engine layout is the transpose: column-major, bit-reversed rows
+    assert nd == 0 or (b.digests == dig[:nd]).all()
+    assert (b.cap == cap).all()
+
+
+@pytest.mark.parametrize("log_n", range(0, 25))
+def test_planner_shapes(emu, log_n):
+    out = np.zeros(6 * 4, np.uint64)
+    for intt in (0, 1):
+        k = emu.emu_plan(135, log_n, 3, intt, out, 4)
+        assert k == (1 if log_n <= 12 else 2)
+        for mode, log_p, log_a, threads, smem, tiles in out.reshape(4, 6)[:k]:
+            assert log_p <= 12 and threads in range(32, 513) and smem <= 200 * 1024 and tiles > 0
+            if mode in (0, 3, 4):                  # strided passes: at least 32-byte segments
+                assert log_a >= 2

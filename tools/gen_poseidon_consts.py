@@ -8,7 +8,8 @@ the round constants and the MDS matrix (factorisation of the partial-round linea
 layer into a sparse matrix per round, Poseidon paper appendix B), then checked
 against the four upstream known-answer vectors in both the naive and the fast form.
 
-Output: oracle/poseidon_consts.h (included by the C oracle and by the .cu files).
+Output: oracle/poseidon_consts.h (C oracle) and eth-lc-plonky2_b200/csrc/poseidon_consts.h (CUDA kernels),
+two identical generated files so that the product never includes anything from oracle/.
 """
 import hashlib
 import os
@@ -260,9 +261,12 @@ def main():
         inp = [rnd.randrange(P) for _ in range(12)]
         assert poseidon_naive(inp, rc) == poseidon_fast(inp, rc, fast)
     here = os.path.dirname(os.path.abspath(__file__))
-    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(here, "..", "oracle", "poseidon_consts.h")
-    emit(out, rc, fast)
-    print("wrote", os.path.normpath(out), "- 4 KATs ok (naive and fast), rc sha256 ok")
+    # the oracle and the product each get their own generated copy: the product never includes from oracle/
+    outs = sys.argv[1:] or [os.path.join(here, "..", "oracle", "poseidon_consts.h"),
+                            os.path.join(here, "..", "eth-lc-plonky2_b200", "csrc", "poseidon_consts.h")]
+    for out in outs:
+        emit(out, rc, fast)
+        print("wrote", os.path.normpath(out), "- 4 KATs ok (naive and fast), rc sha256 ok")
     print("fast K[21] =", fast[1][21], " init[0][:3] =", [hex(x) for x in fast[4][0][:3]])
 
 
