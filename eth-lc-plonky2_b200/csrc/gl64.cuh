@@ -59,30 +59,38 @@ GL_HD u64 gl_sub_c(u64 a, u64 b) {
 }
 GL_HD u64 gl_neg(u64 a) { return gl_sub_c(0, gl_canon(a)); }
 
-// x = lo + hi*2^64, hi = hh*2^32 + hl  ==>  x = lo - hh + hl*(2^32-1)  (mod p)
+// x = lo + hi*2^64 = x0 + x1*2^32 + x2*2^64 + x3*2^96  ==>  x = (x1:x0) + x2*(2^32 - 1) - x3  (mod p).
+// Device path: one 96-bit two's-complement carry chain V = (x1:x0) - x3 - x2 + (x2 << 32), V in (-2^33, 2^65), whose
+// top limb v2 in {-1, 0, 1} is folded back as v2 * (2^32 - 1); neither fold can wrap a second time.
 GL_HD u64 gl_reduce128(u64 lo, u64 hi) {
     u32 x2 = (u32)hi, x3 = (u32)(hi >> 32);
 #ifdef __CUDA_ARCH__
     u32 x0 = (u32)lo, x1 = (u32)(lo >> 32);
-    u32 r0, r1;
-    // (x1:x0) - x3, then - eps when that borrowed (cannot borrow twice).
+    u32 v0, v1;
     asm("{\n\t"
-        ".reg .u32 bw;\n\t"
-        "sub.cc.u32 %0, %2, %4;\n\t"
+        ".reg .u32 v2, t, h;\n\t"
+        "sub.cc.u32  %0, %2, %5;\n\t"
         "subc.cc.u32 %1, %3, 0;\n\t"
-        "subc.u32 bw, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, bw;\n\t"
-        "subc.u32 %1, %1, 0;\n\t"
+        "subc.u32    v2, 0, 0;\n\t"
+        "sub.cc.u32  %0, %0, %4;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32    v2, v2, 0;\n\t"
+        "add.cc.u32  %1, %1, %4;\n\t"
+        "addc.u32    v2, v2, 0;\n\t"
+        "sub.u32     t, 0, v2;\n\t"     // low word of v2*eps  (1 -> 0xffffffff, -1 -> 1)
+        "shr.s32     h, v2, 1;\n\t"     // high word of v2*eps (1 -> 0, -1 -> 0xffffffff)
+        "add.cc.u32  %0, %0, t;\n\t"
+        "addc.u32    %1, %1, h;\n\t"
         "}"
-        : "=r"(r0), "=r"(r1)
-        : "r"(x0), "r"(x1), "r"(x3));
-    u64 r = ((u64)r1 << 32) | r0;
+        : "=&r"(v0), "=&r"(v1)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3));
+    return ((u64)v1 << 32) | v0;
 #else
     u64 r = lo - x3;
     if (lo < x3) r -= GL_EPS;
-#endif
-    u64 t = r + (u64)x2 * GL_EPS;          // one IMAD.WIDE; x2*eps <= 2^64 - 2^33 + 1
+    u64 t = r + (u64)x2 * GL_EPS;          // x2*eps <= 2^64 - 2^33 + 1
     return t + (t < r ? (u64)GL_EPS : 0);  // cannot wrap twice
+#endif
 }
 
 GL_HD u64 gl_mulhi64(u64 a, u64 b) {

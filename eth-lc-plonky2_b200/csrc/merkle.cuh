@@ -53,18 +53,15 @@ GL_HD void merkle_hash_leaf(const MerkleParams &p, u64 j) {
         u64 s[12];
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = 0;
-        u32 full = p.width / 8, tail = p.width % 8;
-        for (u32 c = 0; c < full; c++) {
+        // one (inlined) copy of the permutation: the tail chunk overwrites fewer lanes
+        u32 chunks = (p.width + 7) / 8;
+        PSD_UNROLL1
+        for (u32 c = 0; c < chunks; c++) {
             const u64 *src = row + (u64)(8 * c) * p.col_stride;
-#pragma unroll
-            for (int i = 0; i < 8; i++) s[i] = src[i * p.col_stride];
-            poseidon_permute(s);
-        }
-        if (tail) {
-            const u64 *src = row + (u64)(8 * full) * p.col_stride;
+            u32 len = p.width - 8 * c;
 #pragma unroll
             for (int i = 0; i < 8; i++)
-                if ((u32)i < tail) s[i] = src[i * p.col_stride];
+                if ((u32)i < len) s[i] = src[i * p.col_stride];
             poseidon_permute(s);
         }
 #pragma unroll

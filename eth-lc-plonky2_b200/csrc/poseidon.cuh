@@ -6,6 +6,11 @@
 // identical sparse form (constants derived by tools/gen_poseidon_consts.py and checked against the
 // upstream known-answer vectors).
 //
+// Code-size discipline (profiles/r01_leaves_v0.md): a fully unrolled permutation is ~14 K instructions (217 KB) and
+// the kernel stalled on instruction fetch 13 of every 14 issue slots.  Here every loop is rolled and the
+// per-lane work of a full round runs 3 lanes per iteration with the state ROTATED through the register file
+// (no dynamic register indexing exists), so the hot loops together stay inside the 32 KB instruction cache.
+//
 // Pipe budget per permutation: S-boxes 118 * 4 field products; full-round MDS as
 // 2 * 144 IMAD.WIDE on 32-bit halves (sums < 2^42, one cheap fold per lane); partial rounds as 22 * (11
 // products into a 160-bit accumulator + 11 multiply-adds).
@@ -20,6 +25,7 @@ __constant__ u64 c_fast_k[22];
 __constant__ u64 c_fast_row[22 * 11];
 __constant__ u64 c_fast_col[22 * 11];
 __constant__ u64 c_fast_init[11 * 11];
+__constant__ u32 c_mds[13] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20, 8};  // CIRC[0..12), DIAG[0]
 #endif
 #ifdef __CUDA_ARCH__
 #define PSD_RC(i) c_rc[i]
@@ -28,6 +34,7 @@ __constant__ u64 c_fast_init[11 * 11];
 #define PSD_ROW(i) c_fast_row[i]
 #define PSD_COL(i) c_fast_col[i]
 #define PSD_INIT(i) c_fast_init[i]
+#define PSD_UNROLL1 _Pragma("unroll 1")
 #else
 #define PSD_RC(i) POSEIDON_RC[i]
 #define PSD_FIRST(i) POSEIDON_FAST_FIRST[i]
@@ -35,6 +42,7 @@ __constant__ u64 c_fast_init[11 * 11];
 #define PSD_ROW(i) POSEIDON_FAST_ROW[i]
 #define PSD_COL(i) POSEIDON_FAST_COL[i]
 #define PSD_INIT(i) POSEIDON_FAST_INIT[i]
+#define PSD_UNROLL1
 #endif
 
 #ifdef __CUDACC__
@@ -79,19 +87,66 @@ GL_HD u64 acc160_reduce(const acc160 &acc) {
     return gl_sub_c(r, (u64)acc.top << 32);
 }
 
-// MDS layer: out[r] = sum_i in[(i+r)%12] * CIRC[i] + in[r]*DIAG[r], on 32-bit halves (no reduction inside).
+// MDS layer: out[r] = sum_i in[(i+r)%12] * CIRC[i] + in[r]*DIAG[r], on 32-bit halves (no reduction inside):
+// 2 x 145 IMAD.WIDE with immediate coefficients (written as PTX so that ptxas keeps them as multiply-adds instead
+// of strength-reducing x2/x16 into shift/add chains on the issue-bound alu side), then one 10-instruction fold
+// per lane:  al + ah*2^32 = (a0 - h1) + 2^32 * (a1 + h0 + h1)  (mod p),  al = (a1:a0), ah = (h1:h0) < 2^42.
+#ifdef __CUDA_ARCH__
+// coefficients come from the constant bank (an IMAD.WIDE operand) rather than immediates: with immediates ptxas
+// rewrites x16 / x2 as shift pairs and re-associates the chains into 3-input adds (680 instead of 430 instructions)
+#define PSD_MACW(acc, x, c) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x), "r"(c_mds[c]))
+#define PSD_MULW(acc, x, c) asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(x), "r"(c_mds[c]))
+#define PSD_MDS_ROW(r)                                                                                           \
+    {                                                                                                            \
+        u64 al, ah;                                                                                              \
+        PSD_MULW(al, lo[(0 + r) % 12], 0); PSD_MULW(ah, hi[(0 + r) % 12], 0);                                  \
+        PSD_MACW(al, lo[(1 + r) % 12], 1); PSD_MACW(ah, hi[(1 + r) % 12], 1);                                  \
+        PSD_MACW(al, lo[(2 + r) % 12], 2); PSD_MACW(ah, hi[(2 + r) % 12], 2);                                  \
+        PSD_MACW(al, lo[(3 + r) % 12], 3); PSD_MACW(ah, hi[(3 + r) % 12], 3);                                  \
+        PSD_MACW(al, lo[(4 + r) % 12], 4);  PSD_MACW(ah, hi[(4 + r) % 12], 4);                                   \
+        PSD_MACW(al, lo[(5 + r) % 12], 5); PSD_MACW(ah, hi[(5 + r) % 12], 5);                                  \
+        PSD_MACW(al, lo[(6 + r) % 12], 6); PSD_MACW(ah, hi[(6 + r) % 12], 6);                                  \
+        PSD_MACW(al, lo[(7 + r) % 12], 7); PSD_MACW(ah, hi[(7 + r) % 12], 7);                                  \
+        PSD_MACW(al, lo[(8 + r) % 12], 8); PSD_MACW(ah, hi[(8 + r) % 12], 8);                                  \
+        PSD_MACW(al, lo[(9 + r) % 12], 9); PSD_MACW(ah, hi[(9 + r) % 12], 9);                                  \
+        PSD_MACW(al, lo[(10 + r) % 12], 10); PSD_MACW(ah, hi[(10 + r) % 12], 10);                                \
+        PSD_MACW(al, lo[(11 + r) % 12], 11); PSD_MACW(ah, hi[(11 + r) % 12], 11);                                \
+        if (r == 0) { PSD_MACW(al, lo[0], 12); PSD_MACW(ah, hi[0], 12); }                                          \
+        u32 v0, v1;                                                                                              \
+        asm("{\n\t"                                                                                              \
+            ".reg .u32 a0, a1, h0, h1, t, k, tt, hh;\n\t"                                                        \
+            "mov.b64 {a0, a1}, %2;\n\t"                                                                          \
+            "mov.b64 {h0, h1}, %3;\n\t"                                                                          \
+            "add.u32 t, a1, h1;\n\t"                                                                             \
+            "sub.cc.u32 %0, a0, h1;\n\t"                                                                         \
+            "subc.cc.u32 %1, h0, 0;\n\t"                                                                         \
+            "subc.u32 k, 0, 0;\n\t"                                                                              \
+            "add.cc.u32 %1, %1, t;\n\t"                                                                          \
+            "addc.u32 k, k, 0;\n\t"                                                                              \
+            "sub.u32 tt, 0, k;\n\t"                                                                              \
+            "shr.s32 hh, k, 1;\n\t"                                                                              \
+            "add.cc.u32 %0, %0, tt;\n\t"                                                                         \
+            "addc.u32 %1, %1, hh;\n\t"                                                                           \
+            "}"                                                                                                  \
+            : "=&r"(v0), "=&r"(v1)                                                                               \
+            : "l"(al), "l"(ah));                                                                                 \
+        s[r] = ((u64)v1 << 32) | v0;                                                                             \
+    }
+#endif
 GL_HD void poseidon_mds(u64 (&s)[12]) {
-    const u32 C[12] = POSEIDON_MDS_CIRC_INIT;
     u32 lo[12], hi[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         lo[i] = (u32)s[i];
         hi[i] = (u32)(s[i] >> 32);
     }
-#pragma unroll
+#ifdef __CUDA_ARCH__
+    PSD_MDS_ROW(0) PSD_MDS_ROW(1) PSD_MDS_ROW(2) PSD_MDS_ROW(3) PSD_MDS_ROW(4) PSD_MDS_ROW(5)
+    PSD_MDS_ROW(6) PSD_MDS_ROW(7) PSD_MDS_ROW(8) PSD_MDS_ROW(9) PSD_MDS_ROW(10) PSD_MDS_ROW(11)
+#else
+    const u32 C[12] = POSEIDON_MDS_CIRC_INIT;
     for (int r = 0; r < 12; r++) {
         u64 al = 0, ah = 0;
-#pragma unroll
         for (int i = 0; i < 12; i++) {
             al += (u64)lo[(i + r) % 12] * C[i];
             ah += (u64)hi[(i + r) % 12] * C[i];
@@ -106,30 +161,48 @@ GL_HD void poseidon_mds(u64 (&s)[12]) {
         u64 t = l + (u64)top * GL_EPS;
         s[r] = t + (t < l ? (u64)GL_EPS : 0);
     }
+#endif
 }
 
-GL_HD void poseidon_full_round(u64 (&s)[12], int rc_off) {
+// s <- s rotated left by 3 lanes (register moves; four of these restore the original order)
+GL_HD void poseidon_rot3(u64 (&s)[12]) {
+    u64 a = s[0], b = s[1], c = s[2];
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_pow7(gl_add_c(s[i], PSD_RC(rc_off + i)));
-    poseidon_mds(s);
+    for (int i = 0; i < 9; i++) s[i] = s[i + 3];
+    s[9] = a; s[10] = b; s[11] = c;
+}
+
+// add round constants + S-box on all 12 lanes, 3 lanes per rolled iteration
+GL_HD void poseidon_full_sbox(u64 (&s)[12], int rc_off) {
+    PSD_UNROLL1
+    for (int it = 0; it < 4; it++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) s[k] = gl_pow7(gl_add_c(s[k], PSD_RC(rc_off + 3 * it + k)));
+        poseidon_rot3(s);
+    }
 }
 
 GL_HD void poseidon_partial_rounds(u64 (&s)[12]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], PSD_FIRST(i));
-    {   // dense 11x11 matrix on lanes 1..11 (lane 0 unchanged)
+    {   // dense 11x11 matrix on lanes 1..11 (lane 0 unchanged); rows rolled, outputs shifted through o[]
         u64 o[11];
 #pragma unroll
+        for (int i = 0; i < 11; i++) o[i] = 0;
+        PSD_UNROLL1
         for (int i = 0; i < 11; i++) {
             acc160 acc = {0, 0, 0};
 #pragma unroll
             for (int j = 0; j < 11; j++) acc160_mac(acc, PSD_INIT(11 * i + j), s[j + 1]);
-            o[i] = acc160_reduce(acc);
+            u64 v = acc160_reduce(acc);
+#pragma unroll
+            for (int k = 0; k < 10; k++) o[k] = o[k + 1];
+            o[10] = v;
         }
 #pragma unroll
         for (int i = 0; i < 11; i++) s[i + 1] = o[i];
     }
-#pragma unroll 1
+    PSD_UNROLL1
     for (int r = 0; r < 22; r++) {
         u64 s0 = gl_add_c(gl_pow7(s[0]), PSD_K(r));
         acc160 acc = {0, 0, 0};
@@ -144,11 +217,12 @@ GL_HD void poseidon_partial_rounds(u64 (&s)[12]) {
 
 // The permutation.  Accepts non-canonical lanes; outputs are exact residues, not necessarily canonical.
 GL_HD void poseidon_permute(u64 (&s)[12]) {
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) poseidon_full_round(s, 12 * r);
-    poseidon_partial_rounds(s);
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) poseidon_full_round(s, 12 * (4 + 22 + r));
+    PSD_UNROLL1
+    for (int r = 0; r < 8; r++) {
+        if (r == 4) poseidon_partial_rounds(s);
+        poseidon_full_sbox(s, 12 * (r < 4 ? r : r + 22));
+        poseidon_mds(s);
+    }
 }
 
 // two_to_one(l, r) = permute([l, r, 0, 0, 0, 0])[0..4]
