@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SO = os.path.join(HERE, "libplonky2_b200.so")
+SO = os.environ.get("ENG_SO", os.path.join(HERE, "libplonky2_b200.so"))  # ENG_SO: development A/B builds
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["engine.cu"]
 FLAGS = [
@@ -25,7 +25,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
-    cmd = [NVCC] + FLAGS + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [NVCC] + FLAGS + os.environ.get("ENG_NVCC_EXTRA", "").split() + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

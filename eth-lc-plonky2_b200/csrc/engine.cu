@@ -131,6 +131,7 @@ eng_status launch_mode(const NttLaunch &l) {
     static bool attr_set = false;
     if (!attr_set) {
         CU(cudaFuncSetAttribute(ntt_pass_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(ntt_pass_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     int per_sm = 0;

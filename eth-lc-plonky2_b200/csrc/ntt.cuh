@@ -59,7 +59,9 @@ GL_HD u32 ntt_brev(u32 x, u32 bits) {
 
 GL_HD u32 ntt_pitch(u32 log_p) { u32 P = 1u << log_p; return P + (P >> 4) + 1; }
 GL_HD u32 ntt_sm(u32 pitch, u32 a, u32 j) { return a * pitch + j + (j >> 4); }
-static inline size_t ntt_smem_bytes(u32 log_p, u32 log_a) { return (size_t)ntt_pitch(log_p) * (1u << log_a) * sizeof(u64); }
+static inline size_t ntt_smem_bytes(u32 log_p, u32 log_a) {  // tile + the w_P^e table
+    return ((size_t)ntt_pitch(log_p) * (1u << log_a) + ((1u << log_p) >> 1) + 1) * sizeof(u64);
+}
 
 GL_HD u64 ntt_twiddle2(const NttPass &p, u64 e) {
     u64 lo = p.w_lo[e & ((1ull << p.w_lo_bits) - 1)];
@@ -86,10 +88,7 @@ GL_HD void ntt_load(const NttPass &p, u64 *sm, u64 tile, u32 tid, u32 nthreads) 
         for (u32 idx = tid; idx < total; idx += nthreads) {
             u32 a = idx & (A - 1), j = idx >> p.log_a;
             u64 v = src[((u64)j << log_st) + r0 + a];
-            if (MODE == NTT_LDE_FIRST) {
-                u64 s = gl_mul(p.shift_a[((u64)e << p.log_p) + j], p.shift_b[((u64)e << log_st) + r0 + a]);
-                v = gl_mul(v, s);
-            }
+            if (MODE == NTT_LDE_FIRST) v = gl_mul(v, p.shift_a[((u64)e << p.log_p) + j]);  // s_e^(j*st); s_e^r at the store
             sm[ntt_sm(pitch, a, j)] = v;
         }
     } else if (MODE == NTT_LDE_SINGLE) {
@@ -123,8 +122,10 @@ GL_HD void ntt_load(const NttPass &p, u64 *sm, u64 tile, u32 tid, u32 nthreads) 
 }
 
 // ---- phase 2: one register-blocked round of R DIF stages (stages t0+1 .. t0+R of the P-point network) ----
-template <int R>
-GL_HD void ntt_round(const NttPass &p, u64 *sm, u32 t0, u32 tid, u32 nthreads) {
+// `tw` is the w_P^e table (the kernel stages it in shared memory).  LAST marks the final round (element stride 1):
+// there the twiddle of a butterfly depends only on its register index, and the ones that are 1 are skipped.
+template <int R, bool LAST>
+GL_HD void ntt_round(const NttPass &p, u64 *sm, const u64 *tw, u32 t0, u32 tid, u32 nthreads) {
     const u32 P = 1u << p.log_p, pitch = ntt_pitch(p.log_p);
     const u32 blocks_per_lane = P >> R;
     const u32 nblocks = blocks_per_lane << p.log_a;
@@ -144,10 +145,10 @@ GL_HD void ntt_round(const NttPass &p, u64 *sm, u32 t0, u32 tid, u32 nthreads) {
                 if (m & span) continue;
                 // pair (j, j + half), half = span << log_js; twiddle w_P^{(j mod half) << (t0+u-1)}
                 u32 jm = (((u32)m & (span - 1)) << log_js) + lo;
-                u64 w = p.tw_local[jm << (t0 + u - 1)];
                 u64 x = v[m], y = v[m + span];
                 v[m] = gl_add(x, y);
-                v[m + span] = gl_mul(gl_sub(x, y), w);
+                if (LAST && (m & (span - 1)) == 0) v[m + span] = gl_sub(x, y);  // w = 1
+                else v[m + span] = gl_mul(gl_sub(x, y), tw[jm << (t0 + u - 1)]);
             }
         }
 #pragma unroll
@@ -169,10 +170,26 @@ GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nth
         const u64 r0 = (rem >> p.rate_bits) << p.log_a;
         const u32 b = ntt_brev(e, p.rate_bits);
         u64 *dst = p.out + col * p.out_col_stride + ((u64)b << p.log_n);
-        for (u32 idx = tid; idx < total; idx += nthreads) {
-            u32 a = idx & (A - 1), q = idx >> p.log_a;
-            u64 w = ntt_twiddle2(p, (r0 + a) * (u64)ntt_brev(q, p.log_p));
-            dst[((u64)q << log_st) + r0 + a] = gl_mul(sm[ntt_sm(pitch, a, q)], w);
+        // element (q, a) is multiplied by (s_e * w_n^k1)^(r0+a), k1 = brev(q): one thread walks the A lanes of a slot
+        // with a running power (1 product per element instead of a two-level lookup + the coset factor)
+        const u64 *sb = p.shift_b + ((u64)e << log_st);
+        const u64 se_r0 = sb[r0], se = (log_st ? sb[1] : 1);
+        for (u32 q = tid; q < P; q += nthreads) {
+            u32 k1 = ntt_brev(q, p.log_p);
+            u64 t = gl_mul(ntt_twiddle2(p, r0 * (u64)k1), se_r0);
+            u64 step = gl_mul(p.w_lo[k1], se);
+            u64 *d = dst + ((u64)q << log_st) + r0;
+            for (u32 a = 0; a < A; a += 2) {
+                u64 o0 = gl_mul(sm[ntt_sm(pitch, a, q)], t);
+                t = gl_mul(t, step);
+                u64 o1 = gl_mul(sm[ntt_sm(pitch, a + 1, q)], t);
+                t = gl_mul(t, step);
+#ifdef __CUDA_ARCH__
+                *reinterpret_cast<ulonglong2 *>(d + a) = make_ulonglong2(o0, o1);
+#else
+                d[a] = o0; d[a + 1] = o1;
+#endif
+            }
         }
     } else if (MODE == NTT_LDE_SINGLE) {
         for (u32 idx = tid; idx < total; idx += nthreads) {
@@ -197,10 +214,14 @@ GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nth
         const u64 col = tile / tiles_per_col;
         const u64 r0 = (tile % tiles_per_col) << p.log_a;
         u64 *dst = p.out + col * p.out_col_stride;
-        for (u32 idx = tid; idx < total; idx += nthreads) {
-            u32 k2 = idx & (P - 1), a = idx >> p.log_p;
-            u64 w = ntt_twiddle2(p, (r0 + a) * (u64)k2);
-            dst[((r0 + a) << p.log_p) + k2] = gl_mul(sm[ntt_sm(pitch, a, ntt_brev(k2, p.log_p))], w);
+        for (u32 k2 = tid; k2 < P; k2 += nthreads) {   // running power of w_n^-k2 along the lanes
+            u32 q = ntt_brev(k2, p.log_p);
+            u64 t = ntt_twiddle2(p, r0 * (u64)k2);
+            u64 step = p.w_lo[k2];
+            for (u32 a = 0; a < A; a++) {
+                dst[((r0 + a) << p.log_p) + k2] = gl_mul(sm[ntt_sm(pitch, a, q)], t);
+                t = gl_mul(t, step);
+            }
         }
     } else if (MODE == NTT_INTT_P2) {
         // X[col][k1 * N2 + k0 + a], k1 = brev(q), N2 = 2^log_st, times 1/n
@@ -225,20 +246,35 @@ GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nth
     }
 }
 
+// Runs the rounds of one P-point network: remainder round first, radix-16 rounds after, the last one specialised.
+#define NTT_ROUNDS(SYNC)                                                                                        \
+    {                                                                                                           \
+        u32 t0 = 0;                                                                                             \
+        const u32 rem = p.log_p & 3;                                                                            \
+        if (rem == 1) { if (p.log_p == 1) ntt_round<1, true>(p, sm, tw, t0, tid, nthreads); else ntt_round<1, false>(p, sm, tw, t0, tid, nthreads); t0 += 1; SYNC; } \
+        if (rem == 2) { if (p.log_p == 2) ntt_round<2, true>(p, sm, tw, t0, tid, nthreads); else ntt_round<2, false>(p, sm, tw, t0, tid, nthreads); t0 += 2; SYNC; } \
+        if (rem == 3) { if (p.log_p == 3) ntt_round<3, true>(p, sm, tw, t0, tid, nthreads); else ntt_round<3, false>(p, sm, tw, t0, tid, nthreads); t0 += 3; SYNC; } \
+        for (; t0 + 4 < p.log_p; t0 += 4) { ntt_round<4, false>(p, sm, tw, t0, tid, nthreads); SYNC; }          \
+        if (t0 < p.log_p) { ntt_round<4, true>(p, sm, tw, t0, tid, nthreads); SYNC; }                           \
+    }
+
 #ifdef __CUDACC__
 template <int MODE>
-__global__ void __launch_bounds__(512) ntt_pass_kernel(NttPass p) {
+#ifndef NTT_MINB
+#define NTT_MINB 2
+#endif
+__global__ void __launch_bounds__(512, NTT_MINB) ntt_pass_kernel(NttPass p) {
     extern __shared__ u64 ntt_smem[];
+    u64 *sm = ntt_smem;
+    u64 *tw_s = ntt_smem + (size_t)ntt_pitch(p.log_p) * (1u << p.log_a);   // w_P^e table staged once per CTA
+    const u32 tid = threadIdx.x, nthreads = blockDim.x;
+    for (u32 i = tid; i < ((1u << p.log_p) >> 1); i += nthreads) tw_s[i] = p.tw_local[i];
+    const u64 *tw = tw_s;
     for (u64 tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        ntt_load<MODE>(p, ntt_smem, tile, threadIdx.x, blockDim.x);
+        ntt_load<MODE>(p, sm, tile, tid, nthreads);
         __syncthreads();
-        u32 t0 = 0;
-        u32 rem = p.log_p & 3;
-        if (rem == 1) { ntt_round<1>(p, ntt_smem, t0, threadIdx.x, blockDim.x); t0 += 1; __syncthreads(); }
-        if (rem == 2) { ntt_round<2>(p, ntt_smem, t0, threadIdx.x, blockDim.x); t0 += 2; __syncthreads(); }
-        if (rem == 3) { ntt_round<3>(p, ntt_smem, t0, threadIdx.x, blockDim.x); t0 += 3; __syncthreads(); }
-        for (; t0 < p.log_p; t0 += 4) { ntt_round<4>(p, ntt_smem, t0, threadIdx.x, blockDim.x); __syncthreads(); }
-        ntt_store<MODE>(p, ntt_smem, tile, threadIdx.x, blockDim.x);
+        NTT_ROUNDS(__syncthreads())
+        ntt_store<MODE>(p, sm, tile, tid, nthreads);
         __syncthreads();
     }
 }

@@ -164,22 +164,34 @@ GL_HD void poseidon_mds(u64 (&s)[12]) {
 #endif
 }
 
-// s <- s rotated left by 3 lanes (register moves; four of these restore the original order)
-GL_HD void poseidon_rot3(u64 (&s)[12]) {
-    u64 a = s[0], b = s[1], c = s[2];
+// Lanes handled per rolled iteration of the full-round S-box loop (must divide 12).  The state is ROTATED by that
+// many lanes per iteration so that every iteration addresses the same registers.
+#ifndef PSD_SBOX_LANES
+#define PSD_SBOX_LANES 3
+#endif
+GL_HD void poseidon_rot(u64 (&s)[12]) {
+    u64 t[PSD_SBOX_LANES];
 #pragma unroll
-    for (int i = 0; i < 9; i++) s[i] = s[i + 3];
-    s[9] = a; s[10] = b; s[11] = c;
+    for (int i = 0; i < PSD_SBOX_LANES; i++) t[i] = s[i];
+#pragma unroll
+    for (int i = 0; i < 12 - PSD_SBOX_LANES; i++) s[i] = s[i + PSD_SBOX_LANES];
+#pragma unroll
+    for (int i = 0; i < PSD_SBOX_LANES; i++) s[12 - PSD_SBOX_LANES + i] = t[i];
 }
 
-// add round constants + S-box on all 12 lanes, 3 lanes per rolled iteration
+// add round constants + S-box on all 12 lanes
 GL_HD void poseidon_full_sbox(u64 (&s)[12], int rc_off) {
-    PSD_UNROLL1
-    for (int it = 0; it < 4; it++) {
+#if PSD_SBOX_LANES == 12
 #pragma unroll
-        for (int k = 0; k < 3; k++) s[k] = gl_pow7(gl_add_c(s[k], PSD_RC(rc_off + 3 * it + k)));
-        poseidon_rot3(s);
+    for (int k = 0; k < 12; k++) s[k] = gl_pow7(gl_add_c(s[k], PSD_RC(rc_off + k)));
+#else
+    PSD_UNROLL1
+    for (int it = 0; it < 12 / PSD_SBOX_LANES; it++) {
+#pragma unroll
+        for (int k = 0; k < PSD_SBOX_LANES; k++) s[k] = gl_pow7(gl_add_c(s[k], PSD_RC(rc_off + PSD_SBOX_LANES * it + k)));
+        poseidon_rot(s);
     }
+#endif
 }
 
 GL_HD void poseidon_partial_rounds(u64 (&s)[12]) {
