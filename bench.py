@@ -142,7 +142,8 @@ def workload_config(cols, log_n, gpus):
     return {"workload": "PolynomialBatch::from_values commit, %d Goldilocks columns x 2^%d rows, rate_bits=3, cap_height=4 "
                         "(BASELINE.json configs[1])" % (cols, log_n),
             "columns": cols, "log_rows": log_n, "rate_bits": RATE_BITS, "cap_height": CAP_HEIGHT,
-            "parallelism": "1 GPU" if gpus == 1 else "%d GPUs, one batch per rank (weak)" % gpus,
+            "parallelism": "1 GPU" if gpus == 1 else "%d GPUs: column-sharded iNTT/LDE -> all-to-all -> row-sharded hashing -> cap "
+                                                      "all-gather; rows scale with N (2^20 per GPU)" % gpus,
             "l2": "inputs (%.2f GB per step) are larger than the 126 MB L2; no flush needed" % (8 * cols * (1 << log_n) / 1e9)}
 
 
@@ -175,13 +176,19 @@ def main():
     stream = torch.cuda.Stream()
     E.set_stream(stream.cuda_stream)
 
-    cols, log_n = args.cols, args.log_n
+    cols = args.cols
+    # N = 1: BASELINE configs[1].  N > 1: the same commit column-sharded over the ranks with one all-to-all
+    # (parallel.py); rows scale with N so that the per-GPU work is fixed (weak scaling, configs[4] sweep shape).
+    log_n = args.log_n + (world.bit_length() - 1)
     n = 1 << log_n
+    plan = E.ShardPlan(cols, log_n, RATE_BITS, CAP_HEIGHT, world) if distributed else None
+    my_cols = plan.columns_of(rank) if distributed else range(cols)
     # synthetic witness, generated on the host, pinned for the e2e path
-    host = torch.from_numpy(E.splitmix_columns(cols, n, seed=0x9E3779B97F4A7C15 + rank).view(np.int64)).pin_memory()
+    host = torch.from_numpy(E.splitmix_columns(len(my_cols), n, first_col=my_cols.start).view(np.int64)).pin_memory()
     dev = host.cuda(non_blocking=False)
     host_np = host.numpy().view(np.uint64)
-    host_cols = [host_np[c] for c in range(cols)]
+    host_cols = [host_np[c] for c in range(len(my_cols))]
+    stage_keys = ("IFFT", "FFT + blinding", "transpose LDEs", "build Merkle tree (leaves)", "build Merkle tree (digest levels)", "host to device")
 
     def barrier():
         if distributed:
@@ -189,12 +196,19 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
+        if distributed:
+            b = E.ShardedPolynomialBatch.from_values(dev, plan, rank)
+            return {k: 0.0 for k in stage_keys}
         b = E.PolynomialBatch.from_values(dev, RATE_BITS, False, CAP_HEIGHT)
         ms = b.stage_ms()
         b.close()
         return ms
 
     def step_e2e():
+        if distributed:
+            staged = host.cuda(non_blocking=True)          # H2D of this rank's columns
+            b = E.ShardedPolynomialBatch.from_values(staged, plan, rank)
+            return b.cap                                   # replicated cap, already on the host
         b = E.PolynomialBatch.from_values(host_cols, RATE_BITS, False, CAP_HEIGHT)
         cap = b.merkle_tree.cap            # D2H read of the result
         b.close()
@@ -241,11 +255,25 @@ def main():
     int_peak = E.measure_int_peak()
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        bytes_step = b_ntt(cols, n) * world
+        bytes_step = b_ntt(cols, n)
         ms_step = ms_total / args.steps
         value = bytes_step / (ms_step * 1e-3) / 1e9
         e2e_value = bytes_step / (ms_e2e / args.steps * 1e-3) / 1e9
         stages = {k: v / args.steps for k, v in stage_acc.items()}
+        if distributed:
+            line = {
+                "metric": "commit_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic (SplitMix64 witness columns)",
+                "config": workload_config(cols, log_n, world),
+                "e2e": {"value": e2e_value, "unit": "GB/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": 8 * cols * n, "d2h_bytes_per_step": (32 << CAP_HEIGHT) * world},
+                "gpu_launches": launches, "clocks": clocks, "cap0": "%016x" % int(cap_e2e[0][0]),
+                "exchange": "all_to_all_single of %.2f GB per rank (NCCL), cap all_gather" % (8 * len(my_cols) * (n << RATE_BITS) * (world - 1) / world / 1e9),
+            }
+            print(json.dumps(line))
+            dist.destroy_process_group()
+            return
         leaf_ms = stages["build Merkle tree (leaves)"]
         L = n << RATE_BITS
         leaf_perms = L * ((cols + 7) // 8)

@@ -265,7 +265,7 @@ eng_status make_batch(const uint64_t *const *cols_host, const u64 *src_dev, bool
     }
     CUB(cudaEventRecord(g.ev[2], g.stream));
     plan.clear();
-    if (!ntt_plan_lde(g.tables, b->coeffs, n, b->lde, L, C, log_n, rate_bits, plan)) return bail(fail(ENG_ERR_INVALID, "LDE size unsupported"));
+    if (!ntt_plan_lde(g.tables, b->coeffs, n, b->lde, C, log_n, rate_bits, 0, plan)) return bail(fail(ENG_ERR_INVALID, "LDE size unsupported"));
     STB(launch_plan(plan));
     if (blinding) {
         u64 count = (u64)SALT_SIZE * L;
@@ -485,6 +485,30 @@ eng_status eng_batch_from_coeffs_dev(const uint64_t *coeffs_dev, uint32_t num_po
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!coeffs_dev) return fail(ENG_ERR_INVALID, "coeffs_dev is NULL");
     return make_batch(nullptr, coeffs_dev, false, num_polys, log_n, rate_bits, blinding, blinding_seed, cap_height, out);
+}
+
+eng_status eng_lde_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits, int32_t is_values,
+                       uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *lde_out_dev) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!src_dev || !coeffs_out_dev || !lde_out_dev) return fail(ENG_ERR_INVALID, "NULL buffer");
+    if (num_polys == 0) return fail(ENG_ERR_INVALID, "no polynomials");
+    if (log_n > 2 * NTT_MAX_LOGP || log_n + rate_bits > 32) return fail(ENG_ERR_INVALID, "size unsupported");
+    const u64 n = (u64)1 << log_n;
+    std::vector<NttLaunch> plan;
+    if (is_values) {
+        // the LDE output buffer is the four-step scratch of the iNTT
+        if (!ntt_plan_intt(g.tables, src_dev, n, lde_out_dev, n, coeffs_out_dev, n, num_polys, log_n, plan))
+            return fail(ENG_ERR_INVALID, "iNTT size unsupported");
+        ST(launch_plan(plan));
+    } else if (src_dev != coeffs_out_dev) {
+        CU(cudaMemcpyAsync(coeffs_out_dev, src_dev, (size_t)num_polys * n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+    }
+    plan.clear();
+    if (!ntt_plan_lde(g.tables, coeffs_out_dev, n, lde_out_dev, num_polys, log_n, rate_bits, log_row_shards, plan))
+        return fail(ENG_ERR_INVALID, "LDE shape unsupported (log_n=%u rate_bits=%u log_row_shards=%u)", log_n, rate_bits, log_row_shards);
+    ST(launch_plan(plan));
+    return ENG_OK;
 }
 
 eng_status eng_batch_free(eng_batch *b) {

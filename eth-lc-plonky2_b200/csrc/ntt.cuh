@@ -40,6 +40,12 @@ struct NttPass {
     u64 in_col_stride;   // elements between columns of `in`
     u64 out_col_stride;  // elements between columns of `out`
     u64 num_tiles;     // total work items
+    u64 num_units;     // NTT_DIF_LAST: number of contiguous P-point runs in the buffer
+    // LDE output layout: row k of column c lives at out[(k >> log_shard_rows) * shard_stride + c * out_col_stride +
+    // (k & (2^log_shard_rows - 1))].  One shard (log_shard_rows = log2 L) is the plain [C][L] layout; with G row
+    // shards the buffer is [G][C][L/G], i.e. the all-to-all send chunks of the multi-GPU commit are contiguous.
+    u32 log_shard_rows;
+    u64 shard_stride;
     const u64 *tw_local;  // w_P^e (or inverse), e < P/2
     const u64 *w_lo, *w_hi;  // w_n^e = w_hi[e >> w_lo_bits] * w_lo[e & mask]   (or inverse powers)
     u32 w_lo_bits;
@@ -109,10 +115,8 @@ GL_HD void ntt_load(const NttPass &p, u64 *sm, u64 tile, u32 tid, u32 nthreads) 
             u64 unit = tile * A + a;
             u64 v = 0;
             if (MODE == NTT_DIF_LAST) {
-                // units tile the LDE buffer column by column: unit = col * (L/P) + block-in-column
-                u32 lpc = p.log_n + p.rate_bits - p.log_p;
-                u64 col = unit >> lpc, off = (unit & (((u64)1 << lpc) - 1)) << p.log_p;
-                if (col < p.num_cols) v = p.in[col * p.in_col_stride + off + j];
+                // the LDE buffer is one contiguous array of aligned P-point runs, whatever its shard layout
+                if (unit < p.num_units) v = p.in[(unit << p.log_p) + j];
             } else {
                 if (unit < p.num_cols) v = p.in[unit * p.in_col_stride + j];
             }
@@ -169,7 +173,8 @@ GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nth
         const u32 e = (u32)(rem & ((1u << p.rate_bits) - 1));
         const u64 r0 = (rem >> p.rate_bits) << p.log_a;
         const u32 b = ntt_brev(e, p.rate_bits);
-        u64 *dst = p.out + col * p.out_col_stride + ((u64)b << p.log_n);
+        u64 *dst = p.out + col * p.out_col_stride;
+        const u64 shard_mask = ((u64)1 << p.log_shard_rows) - 1;
         // element (q, a) is multiplied by (s_e * w_n^k1)^(r0+a), k1 = brev(q): one thread walks the A lanes of a slot
         // with a running power (1 product per element instead of a two-level lookup + the coset factor)
         const u64 *sb = p.shift_b + ((u64)e << log_st);
@@ -178,7 +183,8 @@ GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nth
             u32 k1 = ntt_brev(q, p.log_p);
             u64 t = gl_mul(ntt_twiddle2(p, r0 * (u64)k1), se_r0);
             u64 step = gl_mul(p.w_lo[k1], se);
-            u64 *d = dst + ((u64)q << log_st) + r0;
+            u64 k0 = ((u64)b << p.log_n) + ((u64)q << log_st) + r0;   // LDE row of lane 0; the A lanes share its shard
+            u64 *d = dst + (k0 >> p.log_shard_rows) * p.shard_stride + (k0 & shard_mask);
             for (u32 a = 0; a < A; a += 2) {
                 u64 o0 = gl_mul(sm[ntt_sm(pitch, a, q)], t);
                 t = gl_mul(t, step);
@@ -198,15 +204,16 @@ GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nth
             u64 col = unit >> p.rate_bits;
             u32 e = (u32)(unit & ((1u << p.rate_bits) - 1));
             u32 b = ntt_brev(e, p.rate_bits);
-            if (col < p.num_cols) p.out[col * p.out_col_stride + ((u64)b << p.log_n) + q] = gl_canon(sm[ntt_sm(pitch, a, q)]);
+            u64 k = ((u64)b << p.log_n) + q;
+            if (col < p.num_cols)
+                p.out[(k >> p.log_shard_rows) * p.shard_stride + col * p.out_col_stride + (k & (((u64)1 << p.log_shard_rows) - 1))] =
+                    gl_canon(sm[ntt_sm(pitch, a, q)]);
         }
     } else if (MODE == NTT_DIF_LAST) {
         for (u32 idx = tid; idx < total; idx += nthreads) {
             u32 q = idx & (P - 1), a = idx >> p.log_p;
             u64 unit = tile * A + a;
-            u32 lpc = p.log_n + p.rate_bits - p.log_p;
-            u64 col = unit >> lpc, off = (unit & (((u64)1 << lpc) - 1)) << p.log_p;
-            if (col < p.num_cols) p.out[col * p.out_col_stride + off + q] = gl_canon(sm[ntt_sm(pitch, a, q)]);
+            if (unit < p.num_units) p.out[(unit << p.log_p) + q] = gl_canon(sm[ntt_sm(pitch, a, q)]);
         }
     } else if (MODE == NTT_INTT_P1) {
         // Y[col][(r0+a) * P + k2], k2 = brev(q), times w_n^{-(r0+a) k2}

@@ -137,13 +137,19 @@ static inline bool ntt_plan_intt(NttTableStore &ts, const u64 *in, u64 in_stride
     return true;
 }
 
-// coeffs [C][n] -> lde [C][n * 2^r] (column-major, bit-reversed rows), shift 7.
-static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs_stride, u64 *lde, u64 lde_stride, u32 C,
-                                u32 log_n, u32 rate_bits, std::vector<NttLaunch> &plan) {
+// coeffs [C][n] -> lde (column-major, bit-reversed rows), shift 7, as 2^log_shards row shards: [G][C][L/G]
+// (log_shards = 0: the plain [C][L] layout).  Returns false if the shape is unsupported.
+static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs_stride, u64 *lde, u32 C, u32 log_n,
+                                u32 rate_bits, u32 log_shards, std::vector<NttLaunch> &plan) {
     if (log_n > 2 * NTT_MAX_LOGP) return false;
+    const u32 log_l = log_n + rate_bits;
+    if (log_shards > log_l) return false;
     NttPass p = {};
     p.log_n = log_n; p.num_cols = C; p.rate_bits = rate_bits;
-    p.in = coeffs; p.in_col_stride = coeffs_stride; p.out = lde; p.out_col_stride = lde_stride;
+    p.log_shard_rows = log_l - log_shards;
+    p.out_col_stride = (u64)1 << p.log_shard_rows;
+    p.shard_stride = (u64)C << p.log_shard_rows;
+    p.in = coeffs; p.in_col_stride = coeffs_stride; p.out = lde;
     if (log_n <= NTT_MAX_LOGP) {
         auto s = ts.shift(log_n, rate_bits, log_n);  // st = 1: a[e][j] = s_e^j is the whole table
         p.shift_a = s.a; p.shift_b = s.a;
@@ -155,6 +161,7 @@ static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs
         return true;
     }
     u32 lp = ntt_split_first(log_n), lst = log_n - lp;
+    if (lst > p.log_shard_rows) return false;  // a contiguous last-pass run must not straddle row shards
     auto w = ts.w2(log_n, false);
     auto s = ts.shift(log_n, rate_bits, lp);
     p.w_lo = w.lo; p.w_hi = w.hi; p.w_lo_bits = w.lo_bits; p.shift_a = s.a; p.shift_b = s.b;
@@ -163,9 +170,10 @@ static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs
     p.tw_local = ts.tw_local(lp, false);
     plan.push_back(ntt_make_launch(NTT_LDE_FIRST, p));
     // last pass: contiguous runs of 2^lst points, in place over the whole LDE buffer
-    p.in = lde; p.in_col_stride = lde_stride;
+    p.in = lde;
     p.log_p = lst; p.log_a = ntt_log_a_contig(lst);
     u64 units = (u64)C << (log_n + rate_bits - lst);
+    p.num_units = units;
     p.num_tiles = (units + (1u << p.log_a) - 1) >> p.log_a;
     p.tw_local = ts.tw_local(lst, false);
     plan.push_back(ntt_make_launch(NTT_DIF_LAST, p));

@@ -1,0 +1,152 @@
+"""Multi-GPU commit: column-sharded iNTT/LDE -> one all-to-all -> row-sharded Poseidon hashing -> cap all-gather.
+
+SURVEY.md 8(e).  The reference is single-process (rayon threads inside plonky2); this is the B200 design for
+PolynomialBatch::from_values across the GPUs of one box, one process per GPU:
+
+  1. rank r owns a contiguous block of columns; iNTT and coset LDE are independent per column (eng_lde_dev);
+     the LDE is written directly as [G][C_r][L/G] so that slice g -- LDE rows [g*L/G, (g+1)*L/G) in bit-reversed
+     order, i.e. the leaves of row-shard owner g -- is one contiguous send chunk;
+  2. one all-to-all (NCCL over NVLink/NVSwitch; gloo in the CPU tests) turns column shards into row shards:
+     afterwards rank g holds [C][L/G], every column of its L/G leaves;
+  3. rank g hashes its leaves and builds its 2^(cap_height - log2 G) cap sub-trees (eng_merkle_new_dev); the
+     `digests` of the global tree are the concatenation of the per-rank digests in rank order;
+  4. a (2^cap_height x 32 B) all-gather replicates the cap.
+
+Coefficients stay column-sharded, leaves and digests row-sharded.  The local operators are injected (`ops`) so that
+the host-side index logic can be exercised on CPU with gloo; the default operators call the CUDA engine.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineError, check
+
+
+def _log2_strict(x, what):
+    if x <= 0 or x & (x - 1):
+        raise EngineError(_lib.ENG_ERR_INVALID, "%s = %d is not a power of two" % (what, x))
+    return x.bit_length() - 1
+
+
+class ShardPlan:
+    """Who owns what for a batch of `num_polys` columns x 2^log_n rows over `world` ranks."""
+
+    def __init__(self, num_polys, log_n, rate_bits, cap_height, world):
+        self.num_polys, self.log_n, self.rate_bits, self.cap_height, self.world = num_polys, log_n, rate_bits, cap_height, world
+        self.log_world = _log2_strict(world, "world size")
+        self.log_l = log_n + rate_bits
+        if self.log_world > cap_height:
+            raise EngineError(_lib.ENG_ERR_INVALID, "world size %d needs cap_height >= %d (each rank owns whole cap sub-trees)"
+                              % (world, self.log_world))
+        if cap_height > self.log_l:
+            raise EngineError(_lib.ENG_ERR_INVALID, "cap_height %d > log2(leaves) %d" % (cap_height, self.log_l))
+        if num_polys < world:
+            raise EngineError(_lib.ENG_ERR_INVALID, "fewer columns (%d) than ranks (%d)" % (num_polys, world))
+        base, extra = divmod(num_polys, world)
+        self.col_counts = [base + (1 if r < extra else 0) for r in range(world)]
+        self.col_offsets = [sum(self.col_counts[:r]) for r in range(world)]
+        self.rows_per_rank = (1 << self.log_l) >> self.log_world
+        self.local_cap_height = cap_height - self.log_world
+
+    def columns_of(self, rank):
+        return range(self.col_offsets[rank], self.col_offsets[rank] + self.col_counts[rank])
+
+    def owner_of_leaf(self, leaf_index):
+        return leaf_index // self.rows_per_rank, leaf_index % self.rows_per_rank
+
+    def send_splits(self, rank):
+        return [self.col_counts[rank] * self.rows_per_rank] * self.world
+
+    def recv_splits(self):
+        return [c * self.rows_per_rank for c in self.col_counts]
+
+
+class EngineOps:
+    """Local operators backed by the CUDA engine (torch tensors are device memory only)."""
+
+    def __init__(self, device):
+        import torch
+        self.torch, self.device = torch, device
+
+    def empty(self, numel):
+        return self.torch.empty(numel, dtype=self.torch.int64, device=self.device)
+
+    def lde(self, src, is_values, log_n, rate_bits, log_row_shards, coeffs_out, lde_out):
+        num_polys = src.shape[0]
+        check(_lib.lib().eng_lde_dev(C.c_void_p(src.data_ptr()), num_polys, log_n, rate_bits, int(is_values), log_row_shards,
+                                     C.c_void_p(coeffs_out.data_ptr()), C.c_void_p(lde_out.data_ptr())))
+        _lib.synchronize()   # the exchange runs on torch's stream
+
+    def merkle(self, rows_colmajor, num_polys, num_rows, cap_height):
+        from .plonky2 import MerkleTree, _Handle
+        h = C.c_void_p()
+        check(_lib.lib().eng_merkle_new_dev(C.c_void_p(rows_colmajor.data_ptr()), 1, num_rows, num_rows, num_polys, cap_height, C.byref(h)))
+        return MerkleTree(_Handle(h))
+
+    def to_tensor(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to(self.device)
+
+    def to_numpy(self, t):
+        return t.cpu().numpy().view(np.uint64)
+
+
+class ShardedPolynomialBatch:
+    """PolynomialBatch whose polynomials are column-sharded and whose leaves / digests are row-sharded."""
+
+    def __init__(self, plan, rank, coeffs, rows, tree, cap, ops):
+        self.plan, self.rank, self.coeffs, self.rows, self.merkle_tree_local, self.cap, self.ops = plan, rank, coeffs, rows, tree, cap, ops
+
+    @classmethod
+    def from_values(cls, local_values, plan, rank, group=None, ops=None, is_values=True, dist=None):
+        """local_values: [plan.col_counts[rank]][2^log_n] tensor holding this rank's columns (values, or coefficients
+        when is_values is False).  Collective over `group` (torch.distributed)."""
+        if dist is None:
+            import torch.distributed as dist
+        if ops is None:
+            ops = EngineOps(local_values.device)
+        n = 1 << plan.log_n
+        c_r = plan.col_counts[rank]
+        if tuple(local_values.shape) != (c_r, n):
+            raise EngineError(_lib.ENG_ERR_INVALID, "rank %d expects a [%d][%d] column shard, got %s" % (rank, c_r, n, tuple(local_values.shape)))
+        coeffs = ops.empty(c_r * n).view(c_r, n)
+        send = ops.empty(c_r * (n << plan.rate_bits))
+        ops.lde(local_values, is_values, plan.log_n, plan.rate_bits, plan.log_world, coeffs, send)   # [G][C_r][L/G]
+        recv = ops.empty(plan.num_polys * plan.rows_per_rank)                                          # [C][L/G]
+        if plan.world > 1:
+            dist.all_to_all_single(recv, send, output_split_sizes=plan.recv_splits(), input_split_sizes=plan.send_splits(rank), group=group)
+        else:
+            recv.copy_(send)
+        del send
+        tree = ops.merkle(recv, plan.num_polys, plan.rows_per_rank, plan.local_cap_height)
+        local_cap = ops.to_tensor(tree.cap).reshape(-1)
+        if plan.world > 1:
+            parts = [ops.empty(local_cap.numel()) for _ in range(plan.world)]
+            dist.all_gather(parts, local_cap, group=group)
+            cap = np.concatenate([ops.to_numpy(p).reshape(-1, 4) for p in parts])
+        else:
+            cap = ops.to_numpy(local_cap).reshape(-1, 4)
+        return cls(plan, rank, coeffs, recv.view(plan.num_polys, plan.rows_per_rank), tree, cap, ops)
+
+    # ---- accessors for data this rank owns ----
+    def owns_leaf(self, leaf_index):
+        return self.plan.owner_of_leaf(leaf_index)[0] == self.rank
+
+    def get(self, leaf_index):
+        """merkle_tree.get(leaf_index) (only on the owning rank)."""
+        owner, local = self.plan.owner_of_leaf(leaf_index)
+        if owner != self.rank:
+            raise EngineError(_lib.ENG_ERR_INVALID, "leaf %d lives on rank %d" % (leaf_index, owner))
+        return self.merkle_tree_local.get(local)
+
+    def prove(self, leaf_index):
+        """merkle_tree.prove(leaf_index).siblings (only on the owning rank); same siblings as the global tree."""
+        owner, local = self.plan.owner_of_leaf(leaf_index)
+        if owner != self.rank:
+            raise EngineError(_lib.ENG_ERR_INVALID, "leaf %d lives on rank %d" % (leaf_index, owner))
+        return self.merkle_tree_local.prove(local)
+
+    @property
+    def local_digests(self):
+        """This rank's slice of the global `digests` vector (slices concatenate in rank order)."""
+        return self.merkle_tree_local.digests

@@ -77,6 +77,14 @@ eng_status eng_batch_from_coeffs_dev(const uint64_t *coeffs_dev, uint32_t num_po
                                      int32_t blinding, uint64_t blinding_seed, uint32_t cap_height, eng_batch **out);
 eng_status eng_batch_free(eng_batch *b);
 
+/* Multi-GPU building block: iNTT (is_values) + coset LDE of this rank's column shard into
+ * caller-owned device buffers, asynchronously on the engine's stream.  coeffs_out_dev is [num_polys][n];
+ * lde_out_dev is [G][num_polys][L/G] with G = 2^log_row_shards, L = n * 2^rate_bits: slice g holds LDE rows
+ * [g*L/G, (g+1)*L/G) (bit-reversed order) of every local column, i.e. the contiguous all-to-all send chunk for
+ * row-shard owner g.  src_dev may alias coeffs_out_dev.  The receiver hashes its rows with eng_merkle_new_dev. */
+eng_status eng_lde_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits, int32_t is_values,
+                       uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *lde_out_dev);
+
 /* ---- a3: MerkleTree::new(leaves, cap_height)  [plonky2:hash/merkle_tree.rs] ----
  * leaves_host is row-major [num_leaves][leaf_len].  ENG_ERR_INVALID when cap_height > log2(num_leaves) or
  * num_leaves is not a power of two (plonky2 panics). */

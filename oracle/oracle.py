@@ -150,6 +150,9 @@ class Batch:
     def cap(self):
         return self._view(lib().orc_batch_cap(self.h), (1 << self.cap_height, 4))
 
+    def get(self, leaf_index):
+        return self.leaves[leaf_index]
+
     def prove(self, leaf_index):
         sib = np.zeros((64, 4), np.uint64)
         k = lib().orc_batch_prove(self.h, leaf_index, sib)

@@ -67,6 +67,8 @@ static void replay(const std::vector<NttLaunch> &plan, u64 grid) {
 }
 
 extern "C" {
+int emu_batch_sharded(const u64 *values, u32 C, u32 log_n, u32 rate_bits, u32 cap_height, int is_values, u64 grid,
+                      u32 log_shards, u64 *coeffs, u64 *lde, u64 *digests, u64 *cap);
 
 void emu_poseidon_permute(const u64 *in, u64 *out, size_t count) {
     for (size_t i = 0; i < count; i++) {
@@ -84,6 +86,12 @@ u64 emu_gl_sub(u64 a, u64 b) { return gl_canon(gl_sub(a, b)); }
 // values [C][n] -> coeffs [C][n], lde [C][L] (column-major, bit-reversed rows), digests, cap.  Returns 0 on success.
 int emu_batch_from_values(const u64 *values, u32 C, u32 log_n, u32 rate_bits, u32 cap_height, int is_values, u64 grid,
                           u64 *coeffs, u64 *lde, u64 *digests, u64 *cap) {
+    return emu_batch_sharded(values, C, log_n, rate_bits, cap_height, is_values, grid, 0, coeffs, lde, digests, cap);
+}
+
+// same with the LDE written as 2^log_shards row shards [G][C][L/G]; the tree is only built for log_shards = 0
+int emu_batch_sharded(const u64 *values, u32 C, u32 log_n, u32 rate_bits, u32 cap_height, int is_values, u64 grid,
+                      u32 log_shards, u64 *coeffs, u64 *lde, u64 *digests, u64 *cap) {
     NttTableStore ts = make_store();
     const u64 n = (u64)1 << log_n, L = n << rate_bits;
     std::vector<NttLaunch> plan;
@@ -94,8 +102,9 @@ int emu_batch_from_values(const u64 *values, u32 C, u32 log_n, u32 rate_bits, u3
         memcpy(coeffs, values, (size_t)C * n * 8);
     }
     plan.clear();
-    if (!ntt_plan_lde(ts, coeffs, n, lde, L, C, log_n, rate_bits, plan)) return 2;
+    if (!ntt_plan_lde(ts, coeffs, n, lde, C, log_n, rate_bits, log_shards, plan)) return 2;
     replay(plan, grid);
+    if (log_shards) { g_tables.clear(); return 0; }
     MerkleParams mp;
     mp.data = lde; mp.row_stride = 1; mp.col_stride = L; mp.width = C; mp.noop_max = 4; mp.num_leaves = L;
     mp.num_layers = log_n + rate_bits - cap_height; mp.digests = digests; mp.cap = cap;
@@ -112,7 +121,7 @@ int emu_plan(u32 C, u32 log_n, u32 rate_bits, int intt, u64 *out, int max) {
     std::vector<NttLaunch> plan;
     std::vector<u64> dummy(1);
     bool ok = intt ? ntt_plan_intt(ts, dummy.data(), 0, dummy.data(), 0, dummy.data(), 0, C, log_n, plan)
-                   : ntt_plan_lde(ts, dummy.data(), 0, dummy.data(), 0, C, log_n, rate_bits, plan);
+                   : ntt_plan_lde(ts, dummy.data(), 0, dummy.data(), C, log_n, rate_bits, 0, plan);
     g_tables.clear();
     if (!ok) return -1;
     int k = 0;

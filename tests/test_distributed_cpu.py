@@ -1,0 +1,102 @@
+"""world_size-2 (and 4) gloo tests of the multi-GPU commit's host-side logic on CPU.
+
+The sharding / exchange / cap-assembly code of eth-lc-plonky2_b200/parallel.py runs unchanged; only the two local
+operators (column LDE, row hashing) are replaced by oracle-backed stand-ins defined HERE (test infrastructure), because
+this container has no GPU.  The result must equal the single-process oracle commit bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import rand_field
+
+
+class OracleOps:
+    """Stand-in local operators for CPU tests (never used by the product)."""
+
+    def __init__(self):
+        from oracle import oracle as O
+        self.O = O
+
+    def empty(self, numel):
+        return torch.zeros(numel, dtype=torch.int64)
+
+    def lde(self, src, is_values, log_n, rate_bits, log_row_shards, coeffs_out, lde_out):
+        O = self.O
+        vals = src.numpy().view(np.uint64)
+        c_r, n = vals.shape
+        L, G = n << rate_bits, 1 << log_row_shards
+        b = O.Batch.from_values(vals, rate_bits, 0) if is_values else O.Batch.from_coeffs(vals, rate_bits, 0)
+        coeffs_out.copy_(torch.from_numpy(b.coeffs.copy().view(np.int64)))
+        lde = np.ascontiguousarray(b.leaves.T)                    # [C_r][L], bit-reversed rows
+        shards = lde.reshape(c_r, G, L // G).transpose(1, 0, 2)     # [G][C_r][L/G]
+        lde_out.copy_(torch.from_numpy(np.ascontiguousarray(shards).reshape(-1).view(np.int64)))
+
+    def merkle(self, rows_colmajor, num_polys, num_rows, cap_height):
+        rows = rows_colmajor.numpy().view(np.uint64).reshape(num_polys, num_rows).T
+        return self.O.MerkleTree(np.ascontiguousarray(rows), cap_height)
+
+    def to_tensor(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.int64).copy())
+
+    def to_numpy(self, t):
+        return t.numpy().view(np.uint64)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, shape, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import eth_lc_plonky2_b200 as E
+    from oracle import oracle as O
+    C_, log_n, r, h = shape
+    vals = rand_field(np.random.default_rng(42), (C_, 1 << log_n))
+    plan = E.ShardPlan(C_, log_n, r, h, world)
+    cols = plan.columns_of(rank)
+    local = torch.from_numpy(vals[cols.start:cols.stop].copy().view(np.int64))
+    b = E.ShardedPolynomialBatch.from_values(local, plan, rank, ops=OracleOps())
+    ref = O.Batch.from_values(vals, r, h)
+    ok = (b.cap == ref.cap).all()
+    ok &= (b.ops.to_numpy(b.coeffs) == ref.coeffs[cols.start:cols.stop]).all()
+    lo = rank * plan.rows_per_rank
+    ok &= (b.ops.to_numpy(b.rows).T == ref.leaves[lo:lo + plan.rows_per_rank]).all()
+    per = ref.digests.shape[0] // world
+    ok &= (b.local_digests == ref.digests[rank * per:(rank + 1) * per]).all()
+    for k in (lo, lo + plan.rows_per_rank - 1):
+        ok &= b.owns_leaf(k) and (b.prove(k) == ref.prove(k)).all() and (b.get(k) == ref.leaves[k]).all()
+    other = (lo + plan.rows_per_rank) % (1 << plan.log_l)
+    try:
+        b.get(other)
+        ok = False
+    except E.EngineError:
+        pass
+    open(os.path.join(out_dir, "rank%d" % rank), "w").write("ok" if ok else "FAIL")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (9, 5, 3, 4)), (2, (5, 4, 1, 1)), (4, (11, 6, 3, 4)), (2, (135, 4, 3, 4))])
+def test_sharded_commit_matches_single_process(tmp_path, world, shape):
+    mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / ("rank%d" % r)).read() == "ok"
+
+
+def test_shard_plan():
+    import eth_lc_plonky2_b200 as E
+    p = E.ShardPlan(135, 20, 3, 4, 8)
+    assert p.col_counts == [17] * 7 + [16] and p.col_offsets[7] == 119 and p.rows_per_rank == 1 << 20
+    assert p.local_cap_height == 1 and p.owner_of_leaf((1 << 23) - 1) == (7, (1 << 20) - 1)
+    assert sum(p.recv_splits()) == 135 << 20 and p.send_splits(7) == [16 << 20] * 8
+    with pytest.raises(E.EngineError):
+        E.ShardPlan(135, 20, 3, 2, 8)        # 8 ranks cannot own whole sub-trees of a 4-entry cap
+    with pytest.raises(E.EngineError):
+        E.ShardPlan(135, 20, 3, 4, 3)        # not a power of two

@@ -207,3 +207,38 @@ def test_full_size_properties(engine, oracle):
     b8 = engine.PolynomialBatch.from_values(t[:8].contiguous(), r, False, h)
     assert (b8.merkle_tree.cap == o.cap).all()
     assert sha(b8.merkle_tree.leaves(L - 4096, 4096)) == sha(o.leaves[L - 4096:])
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_row_sharded_path_emulated_on_one_gpu(engine, oracle, world):
+    """The kernels of the multi-GPU commit (eng_lde_dev with row shards, eng_merkle_new_dev over a row shard), with the
+    all-to-all replaced by an in-process regrouping: every rank's work runs one after the other on this one GPU."""
+    import torch
+    E = engine
+    C_, log_n, r, h = 21, 13, 3, 4
+    vals = rand_field(np.random.default_rng(world), (C_, 1 << log_n), noncanonical=True)
+    ref = oracle.Batch.from_values(vals, r, h)
+    plan = E.ShardPlan(C_, log_n, r, h, world)
+    ops = E.EngineOps(torch.device("cuda", 0))
+    sends = []
+    for rank in range(world):
+        cols = plan.columns_of(rank)
+        local = ops.to_tensor(vals[cols.start:cols.stop])
+        coeffs = ops.empty(len(cols) << log_n).view(len(cols), 1 << log_n)
+        send = ops.empty(len(cols) << (log_n + r))
+        ops.lde(local, True, log_n, r, plan.log_world, coeffs, send)
+        assert (ops.to_numpy(coeffs) == ref.coeffs[cols.start:cols.stop]).all()
+        sends.append(send.view(world, len(cols), plan.rows_per_rank))
+    caps, per = [], ref.digests.shape[0] // world
+    for g in range(world):
+        recv = torch.cat([sends[p][g] for p in range(world)], dim=0).contiguous()     # what rank g receives: [C][L/G]
+        lo = g * plan.rows_per_rank
+        assert (ops.to_numpy(recv).T == ref.leaves[lo:lo + plan.rows_per_rank]).all()
+        tree = ops.merkle(recv, C_, plan.rows_per_rank, plan.local_cap_height)
+        caps.append(tree.cap)
+        assert (tree.digests == ref.digests[g * per:(g + 1) * per]).all()
+        assert (tree.prove(5) == ref.prove(lo + 5)).all()
+    assert (np.concatenate(caps) == ref.cap).all()
+    if world == 1:
+        b = E.ShardedPolynomialBatch.from_values(ops.to_tensor(vals), plan, 0)
+        assert (b.cap == ref.cap).all() and (b.prove(77) == ref.prove(77)).all()

@@ -88,3 +88,19 @@ def test_planner_shapes(emu, log_n):
             assert log_p <= 12 and threads in range(32, 513) and smem <= 200 * 1024 and tiles > 0
             if mode in (0, 3, 4):                  # strided passes: at least 32-byte segments
                 assert log_a >= 2
+
+
+@pytest.mark.parametrize("C_,log_n,r,log_g", [(5, 4, 3, 1), (5, 4, 3, 3), (3, 13, 3, 3), (3, 13, 3, 2), (2, 13, 1, 3), (7, 6, 2, 3)])
+def test_row_sharded_lde_layout(emu, oracle, C_, log_n, r, log_g):
+    """[G][C][L/G]: slice g is the contiguous all-to-all chunk holding LDE rows [g*L/G, (g+1)*L/G) of every column."""
+    emu.emu_batch_sharded.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.c_uint32, u64p, u64p, u64p, u64p]
+    emu.emu_batch_sharded.restype = C.c_int
+    rng = np.random.default_rng(C_ + log_n)
+    n = 1 << log_n; L = n << r; G = 1 << log_g
+    vals = rand_field(rng, (C_, n))
+    coeffs = np.zeros((C_, n), np.uint64); lde = np.zeros((G, C_, L // G), np.uint64)
+    dummy = np.zeros((1, 4), np.uint64)
+    assert emu.emu_batch_sharded(vals, C_, log_n, r, 0, 1, 3, log_g, coeffs, lde, dummy, dummy) == 0
+    b = oracle.Batch.from_values(vals, r, 0)
+    for g in range(G):
+        assert (lde[g].T == b.leaves[g * (L // G):(g + 1) * (L // G)]).all()
