@@ -57,6 +57,15 @@ _SIGNATURES = {
     "eng_batch_merkle_path": [_vp, C.c_uint64, _vp, C.POINTER(C.c_uint32)],
     "eng_batch_device_ptrs": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
     "eng_batch_stage_ms": [_vp, C.POINTER(C.c_float)],
+    "eng_challenger_new": [C.POINTER(_vp)],
+    "eng_challenger_free": [_vp],
+    "eng_challenger_observe": [_vp, _vp, C.c_size_t],
+    "eng_challenger_get_challenges": [_vp, _vp, C.c_size_t],
+    "eng_challenger_get_state": [_vp, _vp],
+    "eng_challenger_set_state": [_vp, _vp],
+    "eng_batch_eval_ext": [_vp, _vp, _vp],
+    "eng_fri_prove_openings": [_vp, C.POINTER(_vp), C.c_uint32, _vp, C.POINTER(C.c_int32), C.POINTER(_u64p), C.POINTER(C.c_size_t)],
+    "eng_blob_free": [_u64p],
 }
 
 _lib = None

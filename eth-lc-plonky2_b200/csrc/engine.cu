@@ -17,6 +17,7 @@
 #include "microbench.cuh"
 #include "ntt.cuh"
 #include "ntt_plan.h"
+#include "prover.cuh"
 
 #define SALT_SIZE 4u
 
@@ -671,3 +672,5 @@ eng_status eng_batch_stage_ms(const eng_batch *b, float out[6]) {
 }
 
 }  // extern "C"
+
+#include "engine_prover.inc"

@@ -237,3 +237,152 @@ class PolynomialBatch:
 
     def close(self):
         self._o.close()
+
+
+# ---------------------------------------------------------------- a9: Challenger
+class Challenger:
+    """plonky2::iop::challenger::Challenger<F, PoseidonHash> (host-side duplex transcript inside the engine library)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(_lib.load().eng_challenger_new(C.byref(self._h)))
+
+    def observe_elements(self, elements):
+        a = host_u64(np.atleast_1d(elements)).ravel()
+        check(_lib.load().eng_challenger_observe(self._h, ptr(a), a.size))
+
+    observe_element = observe_elements
+    observe_hash = observe_elements               # HashOut: 4 elements
+    observe_cap = observe_elements                # MerkleCap: 2^h hashes, in order
+    observe_extension_element = observe_elements  # to_basefield_array(): [a0, a1]
+    observe_extension_elements = observe_elements
+
+    def get_n_challenges(self, n):
+        out = np.empty(n, np.uint64)
+        check(_lib.load().eng_challenger_get_challenges(self._h, ptr(out), n))
+        return [int(x) for x in out]
+
+    def get_challenge(self):
+        return self.get_n_challenges(1)[0]
+
+    def get_extension_challenge(self):
+        return tuple(self.get_n_challenges(2))
+
+    def get_hash(self):
+        return np.array(self.get_n_challenges(4), np.uint64)
+
+    def state(self):
+        out = np.empty(30, np.uint64)
+        check(_lib.load().eng_challenger_get_state(self._h, ptr(out)))
+        return out
+
+    def set_state(self, st):
+        st = host_u64(st)
+        check(_lib.load().eng_challenger_set_state(self._h, ptr(st)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().eng_challenger_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------- a7 / a8: openings and FRI
+def reduction_arity_bits(degree_bits, rate_bits, cap_height, arity_bits=4, final_poly_bits=5):
+    """FriReductionStrategy::ConstantArityBits(arity_bits, final_poly_bits).reduction_arity_bits(..)."""
+    out = []
+    while degree_bits > final_poly_bits and degree_bits + rate_bits - arity_bits >= cap_height:
+        out.append(arity_bits)
+        degree_bits -= arity_bits
+    return out
+
+
+class FriParams:
+    """plonky2::fri::FriParams (+ the FriConfig fields the prover reads)."""
+
+    def __init__(self, degree_bits, rate_bits=3, cap_height=4, proof_of_work_bits=16, num_query_rounds=28, arity_bits=None):
+        self.degree_bits, self.rate_bits, self.cap_height = degree_bits, rate_bits, cap_height
+        self.proof_of_work_bits, self.num_query_rounds = proof_of_work_bits, num_query_rounds
+        self.reduction_arity_bits = reduction_arity_bits(degree_bits, rate_bits, cap_height) if arity_bits is None else list(arity_bits)
+
+    def as_array(self):
+        v = [self.degree_bits, self.rate_bits, self.cap_height, self.proof_of_work_bits, self.num_query_rounds,
+             len(self.reduction_arity_bits)] + self.reduction_arity_bits
+        return (C.c_int32 * len(v))(*v)
+
+
+class FriInstanceInfo:
+    """plonky2::fri::structure::FriInstanceInfo: batches = [(point (a, b), [(oracle_index, polynomial_index), ...]), ...]."""
+
+    def __init__(self, batches):
+        self.batches = batches
+
+    def blob(self):
+        o = [len(self.batches)]
+        for point, polys in self.batches:
+            o += [int(point[0]), int(point[1]), len(polys)] + [(int(a) << 32) | int(b) for a, b in polys]
+        return np.array(o, np.uint64)
+
+
+class FriProof:
+    """plonky2::fri::proof::FriProof as the engine's flat blob (layout in include/plonky2_b200.h), parsed lazily."""
+
+    def __init__(self, blob):
+        self.blob = blob
+        i = 0
+        b = [int(x) for x in blob]
+        r = b[i]; i += 1
+        self.commit_phase_merkle_caps = []
+        for _ in range(r):
+            n = b[i]; i += 1
+            self.commit_phase_merkle_caps.append(np.array(b[i:i + n], np.uint64).reshape(-1, 4)); i += n
+        f = b[i]; i += 1
+        self.final_poly = np.array(b[i:i + 2 * f], np.uint64).reshape(-1, 2); i += 2 * f
+        self.pow_witness = b[i]; i += 1
+        q = b[i]; i += 1
+        self.query_round_proofs = []
+        for _ in range(q):
+            o = b[i]; i += 1
+            initial = []
+            for _ in range(o):
+                n = b[i]; i += 1
+                leaf = np.array(b[i:i + n], np.uint64); i += n
+                n = b[i]; i += 1
+                path = np.array(b[i:i + 4 * n], np.uint64).reshape(-1, 4); i += 4 * n
+                initial.append((leaf, path))
+            s = b[i]; i += 1
+            steps = []
+            for _ in range(s):
+                n = b[i]; i += 1
+                evals = np.array(b[i:i + 2 * n], np.uint64).reshape(-1, 2); i += 2 * n
+                n = b[i]; i += 1
+                path = np.array(b[i:i + 4 * n], np.uint64).reshape(-1, 4); i += 4 * n
+                steps.append((evals, path))
+            self.query_round_proofs.append((initial, steps))
+        assert i == len(b)
+
+
+def _eval_batch(self, z):
+    """eval_commitment(z, self) of OpeningSet::new: every polynomial at z = (a, b) in F_p^2 -> [num_polys][2]."""
+    zz = host_u64([int(z[0]), int(z[1])])
+    out = np.empty((self._o.info.num_polys, 2), np.uint64)
+    check(_lib.lib().eng_batch_eval_ext(self._o._h, ptr(zz), ptr(out)))
+    return out
+
+
+def _prove_openings(instance, oracles, challenger, fri_params, timing=None):
+    """PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params, timing) -> FriProof."""
+    hs = (C.c_void_p * len(oracles))(*[o._o._h for o in oracles])
+    inst = instance.blob()
+    blob = C.POINTER(C.c_uint64)()
+    n = C.c_size_t(0)
+    check(_lib.lib().eng_fri_prove_openings(ptr(inst), hs, len(oracles), challenger._h, fri_params.as_array(), C.byref(blob), C.byref(n)))
+    out = np.ctypeslib.as_array(blob, shape=(n.value,)).copy()
+    _lib.lib().eng_blob_free(blob)
+    return FriProof(out)
+
+
+PolynomialBatch.eval = _eval_batch
+PolynomialBatch.prove_openings = staticmethod(_prove_openings)

@@ -125,6 +125,36 @@ eng_status eng_batch_device_ptrs(const eng_batch *b, const uint64_t **lde_dev, c
  * [3] "build Merkle tree" leaf hashing  [4] "build Merkle tree" digest levels + cap  [5] host->device copies */
 eng_status eng_batch_stage_ms(const eng_batch *b, float out[6]);
 
+/* ---- a9: Challenger<F, PoseidonHash>  [plonky2:iop/challenger.rs] ----
+ * Host-side duplex transcript (one permutation per 8 observed elements), bit-compatible with plonky2's: the state
+ * crosses the FFI as 30 words: [0..12) sponge_state, [12] input_buffer.len(), [13..21) input_buffer,
+ * [21] output_buffer.len(), [22..30) output_buffer. */
+typedef struct eng_challenger eng_challenger;
+eng_status eng_challenger_new(eng_challenger **out);
+eng_status eng_challenger_free(eng_challenger *c);
+eng_status eng_challenger_observe(eng_challenger *c, const uint64_t *elements, size_t n);   /* observe_elements */
+eng_status eng_challenger_get_challenges(eng_challenger *c, uint64_t *out, size_t n);       /* get_n_challenges */
+eng_status eng_challenger_get_state(const eng_challenger *c, uint64_t out[30]);
+eng_status eng_challenger_set_state(eng_challenger *c, const uint64_t in[30]);
+
+/* ---- a7: OpeningSet::new's eval_commitment(z, batch)  [plonky2:plonk/proof.rs] ----
+ * Evaluates every polynomial of the batch at z = z[0] + z[1]*X in F_p^2; out_host is [num_polys][2]. */
+eng_status eng_batch_eval_ext(const eng_batch *b, const uint64_t z[2], uint64_t *out_host);
+
+/* ---- a8: PolynomialBatch::prove_openings -> fri_proof  [plonky2:fri/oracle.rs, fri/prover.rs] ----
+ * instance (FriInstanceInfo): [num_batches] then per batch [point.a, point.b, num_polys, (oracle_index << 32 |
+ *   polynomial_index) x num_polys].
+ * params (FriParams): [degree_bits, rate_bits, cap_height, proof_of_work_bits, num_query_rounds,
+ *   reduction_arity_bits.len(), reduction_arity_bits...]  (arity 16 only: ConstantArityBits(4, _)).
+ * The challenger must be in the state right after observing the openings; it is advanced exactly as plonky2's.
+ * Output (FriProof), a malloc'ed flat u64 array released with eng_blob_free (NOT plonky2's wire format, row f4):
+ *   [R] R x { [len] cap } | [F] F x (a, b) final_poly | pow_witness |
+ *   [Q] Q x { [O] O x { [leaf_len] leaf | [path_len] path x 4 } | [R] R x { [arity] evals x 2 | [path_len] path x 4 } }
+ * pow_witness is the SMALLEST valid witness (plonky2's rayon find_any returns an arbitrary one). */
+eng_status eng_fri_prove_openings(const uint64_t *instance, const eng_batch *const *oracles, uint32_t num_oracles,
+                                  eng_challenger *challenger, const int32_t *params, uint64_t **blob_out, size_t *blob_len);
+eng_status eng_blob_free(uint64_t *blob);
+
 #ifdef __cplusplus
 }
 #endif

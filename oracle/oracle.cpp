@@ -5,6 +5,7 @@
 #include <omp.h>
 #include "commit.h"
 #include "challenger.h"
+#include "fri.h"
 
 double orc_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -72,5 +73,71 @@ void *orc_challenger_new() { OrcChallenger *c = new OrcChallenger(); orc_ch_init
 void orc_challenger_free(void *c) { delete (OrcChallenger *)c; }
 void orc_challenger_observe(void *c, const u64 *e, size_t n) { orc_ch_observe_n((OrcChallenger *)c, e, n); }
 u64 orc_challenger_get(void *c) { return orc_ch_challenge((OrcChallenger *)c); }
+
+
+/* ---- openings + FRI ----
+ * instance blob: [num_batches] then per batch [point.a, point.b, num_polys, (oracle << 32 | poly) x num_polys]
+ * params: [degree_bits, rate_bits, cap_height, pow_bits, num_query_rounds, num_arity, arity_bits...] */
+static std::vector<OrcFriBatchInfo> parse_instance(const u64 *b) {
+    std::vector<OrcFriBatchInfo> out;
+    size_t i = 0;
+    u64 nb = b[i++];
+    for (u64 k = 0; k < nb; k++) {
+        OrcFriBatchInfo bi;
+        bi.point = gl2_make(b[i], b[i + 1]); i += 2;
+        u64 np = b[i++];
+        for (u64 j = 0; j < np; j++) { OrcFriPolyRef r = {(int)(b[i] >> 32), (int)(b[i] & 0xffffffffu)}; bi.polys.push_back(r); i++; }
+        out.push_back(bi);
+    }
+    return out;
+}
+static OrcFriParams parse_params(const int *p) {
+    OrcFriParams P;
+    P.degree_bits = p[0]; P.rate_bits = p[1]; P.cap_height = p[2]; P.pow_bits = p[3]; P.num_query_rounds = p[4];
+    for (int i = 0; i < p[5]; i++) P.arity_bits.push_back(p[6 + i]);
+    return P;
+}
+void orc_batch_eval_c(void *h, const u64 *z, u64 *out) {
+    vec2 v = orc_batch_eval(*(OrcBatch *)h, gl2_make(gl_canon(z[0]), gl_canon(z[1])));
+    for (size_t i = 0; i < v.size(); i++) { out[2 * i] = v[i].a; out[2 * i + 1] = v[i].b; }
+}
+int orc_fri_arity_bits_c(int degree_bits, int rate_bits, int cap_height, int arity_bits, int final_poly_bits, int *out) {
+    std::vector<int> r = orc_fri_reduction_arity_bits(degree_bits, rate_bits, cap_height, arity_bits, final_poly_bits);
+    for (size_t i = 0; i < r.size(); i++) out[i] = r[i];
+    return (int)r.size();
+}
+void *orc_fri_prove_c(const u64 *instance, void **oracles, int num_oracles, void *challenger, const int *params) {
+    std::vector<const OrcBatch *> os;
+    for (int i = 0; i < num_oracles; i++) os.push_back((const OrcBatch *)oracles[i]);
+    OrcFriProof p = orc_fri_prove(parse_instance(instance), os, (OrcChallenger *)challenger, parse_params(params));
+    return new vec64(orc_fri_proof_blob(p));
+}
+size_t orc_blob_len(void *b) { return ((vec64 *)b)->size(); }
+const u64 *orc_blob_data(void *b) { return ((vec64 *)b)->data(); }
+void orc_blob_free(void *b) { delete (vec64 *)b; }
+/* openings: per batch, the claimed values in instance order, flattened [(a, b)...]; caps: num_oracles x (2^h * 4) */
+int orc_fri_verify_c(const u64 *instance, const u64 *openings, const u64 *caps, const int *leaf_lens, int num_oracles,
+                     const u64 *proof_blob, size_t proof_len, void *challenger, const int *params) {
+    std::vector<OrcFriBatchInfo> inst = parse_instance(instance);
+    OrcFriParams P = parse_params(params);
+    std::vector<vec2> ops;
+    size_t i = 0;
+    for (const OrcFriBatchInfo &b : inst) {
+        vec2 v;
+        for (size_t j = 0; j < b.polys.size(); j++) { v.push_back(gl2_make(openings[i], openings[i + 1])); i += 2; }
+        ops.push_back(v);
+    }
+    std::vector<vec64> cps;
+    std::vector<int> lens;
+    size_t capsz = (size_t)4 << P.cap_height;
+    for (int o = 0; o < num_oracles; o++) { cps.emplace_back(caps + o * capsz, caps + (o + 1) * capsz); lens.push_back(leaf_lens[o]); }
+    OrcFriProof p;
+    if (!orc_fri_proof_from_blob(proof_blob, proof_len, p)) return 100;
+    return orc_fri_verify(inst, ops, cps, lens, p, (OrcChallenger *)challenger, P);
+}
+void orc_challenger_state(void *c, u64 *out /* 12 state + 1 n_in + 8 in + 1 n_out + 8 out */) {
+    OrcChallenger *ch = (OrcChallenger *)c;
+    memcpy(out, ch->state, 96); out[12] = ch->n_in; memcpy(out + 13, ch->in_buf, 64); out[21] = ch->n_out; memcpy(out + 22, ch->out_buf, 64);
+}
 
 } /* extern "C" */

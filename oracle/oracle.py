@@ -58,6 +58,17 @@ def lib():
         L.orc_challenger_free.argtypes = [C.c_void_p]
         L.orc_challenger_observe.argtypes = [C.c_void_p, _u64p, C.c_size_t]
         L.orc_challenger_get.restype = C.c_uint64; L.orc_challenger_get.argtypes = [C.c_void_p]
+        L.orc_batch_eval_c.argtypes = [C.c_void_p, _u64p, _u64p]
+        L.orc_fri_arity_bits_c.restype = C.c_int
+        L.orc_fri_arity_bits_c.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_int)]
+        L.orc_fri_prove_c.restype = C.c_void_p
+        L.orc_fri_prove_c.argtypes = [_u64p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.orc_blob_len.restype = C.c_size_t; L.orc_blob_len.argtypes = [C.c_void_p]
+        L.orc_blob_data.restype = C.POINTER(C.c_uint64); L.orc_blob_data.argtypes = [C.c_void_p]
+        L.orc_blob_free.argtypes = [C.c_void_p]
+        L.orc_fri_verify_c.restype = C.c_int
+        L.orc_fri_verify_c.argtypes = [_u64p, _u64p, _u64p, C.POINTER(C.c_int), C.c_int, _u64p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]
+        L.orc_challenger_state.argtypes = [C.c_void_p, _u64p]
         _lib = L
     return _lib
 
@@ -195,9 +206,60 @@ class Challenger:
     def get_n_challenges(self, n):
         return [self.get_challenge() for _ in range(n)]
 
+    def get_extension_challenge(self):
+        return (self.get_challenge(), self.get_challenge())
+
+    def state(self):
+        out = np.zeros(30, np.uint64)
+        lib().orc_challenger_state(self.h, out)
+        return out
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_challenger_free(self.h); self.h = None
+
+
+def batch_eval(batch, z):
+    """eval_commitment(z, batch): every polynomial of the batch at z in F_p^2 -> [C][2]."""
+    out = np.zeros((batch.C, 2), np.uint64)
+    lib().orc_batch_eval_c(batch.h, _a(z), out)
+    return out
+
+
+def fri_arity_bits(degree_bits, rate_bits=3, cap_height=4, arity_bits=4, final_poly_bits=5):
+    out = (C.c_int * 32)()
+    k = lib().orc_fri_arity_bits_c(degree_bits, rate_bits, cap_height, arity_bits, final_poly_bits, out)
+    return list(out[:k])
+
+
+def fri_instance_blob(batches):
+    """batches: [(point (a, b), [(oracle, poly), ...]), ...] -> flat u64 description shared with the engine."""
+    o = [len(batches)]
+    for point, polys in batches:
+        o += [int(point[0]), int(point[1]), len(polys)] + [(int(a) << 32) | int(b) for a, b in polys]
+    return np.array(o, np.uint64)
+
+
+def fri_params_array(degree_bits, rate_bits, cap_height, pow_bits, num_query_rounds, arity_bits):
+    v = [degree_bits, rate_bits, cap_height, pow_bits, num_query_rounds, len(arity_bits)] + list(arity_bits)
+    return (C.c_int * len(v))(*v)
+
+
+def fri_prove(instance_blob, oracles, challenger, params):
+    hs = (C.c_void_p * len(oracles))(*[o.h for o in oracles])
+    b = lib().orc_fri_prove_c(_a(instance_blob), hs, len(oracles), challenger.h, params)
+    n = lib().orc_blob_len(b)
+    out = np.ctypeslib.as_array(lib().orc_blob_data(b), shape=(n,)).copy()
+    lib().orc_blob_free(b)
+    return out
+
+
+def fri_verify(instance_blob, openings, caps, leaf_lens, proof_blob, challenger, params):
+    """0 = verifies; otherwise the code of the failed check (see oracle/fri.h::orc_fri_verify)."""
+    ll = (C.c_int * len(leaf_lens))(*leaf_lens)
+    proof_blob = _a(proof_blob)
+    return lib().orc_fri_verify_c(_a(instance_blob), _a(openings).ravel(), _a(caps).ravel(), ll, len(leaf_lens), proof_blob,
+                                  proof_blob.size, challenger.h, params)
 
 
 def splitmix_columns(C_, n, seed=0x9E3779B97F4A7C15):
