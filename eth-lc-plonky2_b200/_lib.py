@@ -66,6 +66,12 @@ _SIGNATURES = {
     "eng_batch_eval_ext": [_vp, _vp, _vp],
     "eng_fri_prove_openings": [_vp, C.POINTER(_vp), C.c_uint32, _vp, C.POINTER(C.c_int32), C.POINTER(_u64p), C.POINTER(C.c_size_t)],
     "eng_blob_free": [_u64p],
+    "eng_circuit_new": [_vp, _vp, C.POINTER(_vp), C.POINTER(_vp)],
+    "eng_circuit_free": [_vp],
+    "eng_partial_products": [_vp, C.POINTER(_vp), _vp, _vp, _vp],
+    "eng_quotient": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)],
+    "eng_prove": [_vp, C.POINTER(_vp), _vp, C.POINTER(_u64p), C.POINTER(C.c_size_t), C.POINTER(C.c_float)],
+    "eng_synth_circuit": [C.c_uint32, C.c_uint64, _vp, _vp, _vp, _vp, _vp],
 }
 
 _lib = None

@@ -18,6 +18,8 @@
 #include "ntt.cuh"
 #include "ntt_plan.h"
 #include "prover.cuh"
+#include "plonk.cuh"
+#include <map>
 
 #define SALT_SIZE 4u
 
@@ -58,6 +60,7 @@ struct Ctx {
     std::vector<void *> table_allocs;
     uint64_t launches = 0;
     cudaEvent_t ev[8] = {};
+    std::map<std::pair<u64, u32>, NttTableStore::W2> pow_cache;   // two-level power tables of arbitrary bases
 };
 Ctx g;
 
@@ -337,7 +340,7 @@ eng_status eng_shutdown(void) {
     cudaDeviceSynchronize();
     for (void *p : g.table_allocs) cudaFree(p);
     g.table_allocs.clear();
-    g.tables.tw_local_cache.clear(); g.tables.w2_cache.clear(); g.tables.shift_cache.clear();
+    g.tables.tw_local_cache.clear(); g.tables.w2_cache.clear(); g.tables.shift_cache.clear(); g.pow_cache.clear();
     for (auto &ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
     if (g.own_stream) cudaStreamDestroy(g.own_stream);
     g.own_stream = g.stream = nullptr;
@@ -674,3 +677,4 @@ eng_status eng_batch_stage_ms(const eng_batch *b, float out[6]) {
 }  // extern "C"
 
 #include "engine_prover.inc"
+#include "engine_plonk.inc"

@@ -18,7 +18,7 @@
 #pragma once
 #include "gl64.cuh"
 
-#define NTT_MAX_LOGP 12
+#define NTT_MAX_LOGP 13
 
 enum NttMode : int {
     NTT_LDE_FIRST = 0,   // coeffs (strided tile) * shift powers -> DIF -> * w_n^{r k1} -> block b, in-place order

@@ -81,10 +81,11 @@ static inline uint32_t ntt_threads(u32 log_p, u32 log_a) {
     u32 t = blocks < 32 ? 32 : blocks;
     return t > 512 ? 512 : t;
 }
-// lanes per tile: ~8K elements per tile (16K once P >= 2^11), never fewer than 4 lanes (32-byte segments)
+// lanes per tile: ~8K elements per tile (16K once P >= 2^11), never fewer than 4 lanes (32-byte segments) below 2^13
 static inline u32 ntt_log_a_strided(u32 log_p, u32 log_st) {
     u32 la = log_p >= 13 ? 0 : 13 - log_p;
-    if (la < 2) la = 2;
+    const u32 la_min = log_p >= 13 ? 1 : 2;   // 2^13-point tiles only fit two lanes in shared memory
+    if (la < la_min) la = la_min;
     if (la > 6) la = 6;
     if (la > log_st) la = log_st;
     return la;

@@ -386,3 +386,79 @@ def _prove_openings(instance, oracles, challenger, fri_params, timing=None):
 
 PolynomialBatch.eval = _eval_batch
 PolynomialBatch.prove_openings = staticmethod(_prove_openings)
+
+
+# ---------------------------------------------------------------- a5 / a6 / prove
+def synth_circuit(degree_bits, seed=1):
+    """Synthetic circuit over the five core gates with a satisfying witness (eng_synth_circuit; host code, no GPU).
+    Returns dict(blob, constants [4][n], sigmas [80][n], wires [135][n], pi_hash [4])."""
+    n = 1 << degree_bits
+    out = dict(constants=np.zeros((4, n), np.uint64), sigmas=np.zeros((80, n), np.uint64), wires=np.zeros((135, n), np.uint64),
+               pi_hash=np.zeros(4, np.uint64), blob=np.zeros(36, np.uint64))
+    check(_lib.load().eng_synth_circuit(degree_bits, seed, ptr(out["constants"]), ptr(out["sigmas"]), ptr(out["wires"]),
+                                        ptr(out["pi_hash"]), ptr(out["blob"])))
+    return out
+
+
+def _col_ptrs(cols):
+    cols = [host_u64(c) for c in cols]
+    return cols, (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+
+
+class Circuit:
+    """What the plonk rows need of plonky2's CommonCircuitData / ProverOnlyCircuitData, resident on the device."""
+
+    def __init__(self, blob, constants_sigmas, sigma_values):
+        self.blob = host_u64(blob)
+        b = [int(x) for x in self.blob]
+        (self.degree_bits, self.num_wires, self.num_routed, self.num_gate_constants, self.num_selectors, self.num_challenges,
+         self.quotient_degree_factor, self.rate_bits, self.cap_height) = b[:9]
+        self.num_partial_products = (self.num_routed + self.quotient_degree_factor - 1) // self.quotient_degree_factor - 1
+        self.constants_sigmas = constants_sigmas
+        keep, ptrs = _col_ptrs(sigma_values)
+        self._h = C.c_void_p()
+        check(_lib.lib().eng_circuit_new(ptr(self.blob), constants_sigmas._o._h, ptrs, C.byref(self._h)))
+
+    @classmethod
+    def build(cls, synth, rate_bits=3, cap_height=4):
+        """The part of CircuitBuilder::build() on the hot path: commit constants || sigmas."""
+        cs = PolynomialBatch.from_values(list(synth["constants"]) + list(synth["sigmas"]), rate_bits, False, cap_height)
+        return cls(synth["blob"], cs, synth["sigmas"])
+
+    def partial_products(self, wire_values, betas, gammas):
+        """all_wires_permutation_partial_products -> [num_challenges*(1+num_partial_products)][n], committed order."""
+        keep, ptrs = _col_ptrs(wire_values)
+        n = 1 << self.degree_bits
+        out = np.empty((self.num_challenges * (1 + self.num_partial_products), n), np.uint64)
+        b, g_ = host_u64(betas), host_u64(gammas)
+        check(_lib.lib().eng_partial_products(self._h, ptrs, ptr(b), ptr(g_), ptr(out)))
+        return out
+
+    def quotient(self, wires_batch, zs_pp_batch, public_inputs_hash, betas, gammas, alphas):
+        """compute_quotient_polys + split + commit -> PolynomialBatch of num_challenges*8 chunk polynomials."""
+        h = C.c_void_p()
+        pi, b, g_, a = host_u64(public_inputs_hash), host_u64(betas), host_u64(gammas), host_u64(alphas)
+        check(_lib.lib().eng_quotient(self._h, wires_batch._o._h, zs_pp_batch._o._h, ptr(pi), ptr(b), ptr(g_), ptr(a), C.byref(h)))
+        return PolynomialBatch(_Handle(h))
+
+    def prove(self, wire_values, public_inputs_hash):
+        """prove_with_partition_witness after witness generation -> (proof blob, stage milliseconds)."""
+        keep, ptrs = _col_ptrs(wire_values)
+        pi = host_u64(public_inputs_hash)
+        blob = C.POINTER(C.c_uint64)()
+        n = C.c_size_t(0)
+        ms = (C.c_float * 8)()
+        check(_lib.lib().eng_prove(self._h, ptrs, ptr(pi), C.byref(blob), C.byref(n), ms))
+        out = np.ctypeslib.as_array(blob, shape=(n.value,)).copy()
+        _lib.lib().eng_blob_free(blob)
+        names = ("wires commitment", "partial products", "Z commitment", "quotient polys", "quotient commitment", "opening set",
+                 "opening proofs (FRI)", "total")
+        return out, dict(zip(names, list(ms)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().eng_circuit_free(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -155,6 +155,46 @@ eng_status eng_fri_prove_openings(const uint64_t *instance, const eng_batch *con
                                   eng_challenger *challenger, const int32_t *params, uint64_t **blob_out, size_t *blob_len);
 eng_status eng_blob_free(uint64_t *blob);
 
+/* ---- circuit handle for the plonk rows ----
+ * blob (what the rows need of CommonCircuitData / ProverOnlyCircuitData): [degree_bits, num_wires, num_routed_wires,
+ *   num_constants (gate constants, without selectors), num_selectors, num_challenges, quotient_degree_factor, rate_bits,
+ *   cap_height, proof_of_work_bits, num_query_rounds, num_gates, (gate_kind, selector_index, group.start, group.end)
+ *   x num_gates (gates in plonky2's degree-sorted order), circuit_digest x 4].
+ * gate_kind: 0 NoopGate, 1 ConstantGate{2}, 2 PublicInputGate, 3 ArithmeticGate{20}, 4 PoseidonGate.
+ * constants_sigmas: the batch committed by build() (selectors, gate constants, sigmas -- in that column order);
+ * sigma_cols_host: the sigma polynomials' values on the subgroup (prover_data.sigmas, column j = routed wire j). */
+typedef struct eng_circuit eng_circuit;
+eng_status eng_circuit_new(const uint64_t *blob, const eng_batch *constants_sigmas, const uint64_t *const *sigma_cols_host,
+                           eng_circuit **out);
+eng_status eng_circuit_free(eng_circuit *c);
+
+/* ---- a5: all_wires_permutation_partial_products  [plonky2:plonk/prover.rs] ----
+ * wire_cols_host: the full witness (num_wires columns, only the routed ones are read).  out_host:
+ * [num_challenges * (1 + num_partial_products)][n] in the order prove() commits them: Z_0.., pp_0[..], pp_1[..]. */
+eng_status eng_partial_products(const eng_circuit *c, const uint64_t *const *wire_cols_host, const uint64_t *betas,
+                                const uint64_t *gammas, uint64_t *out_host);
+
+/* ---- a6: compute_quotient_polys + "split up" + "commit to quotient polys"  [plonky2:plonk/prover.rs] ----
+ * Returns the committed batch of num_challenges * quotient_degree_factor chunk polynomials. */
+eng_status eng_quotient(const eng_circuit *c, const eng_batch *wires, const eng_batch *zs_partial_products,
+                        const uint64_t *public_inputs_hash, const uint64_t *betas, const uint64_t *gammas,
+                        const uint64_t *alphas, eng_batch **quotient_out);
+
+/* ---- prove_with_partition_witness after witness generation  [plonky2:plonk/prover.rs] ----
+ * Everything between "compute full witness" and the returned proof, device-resident between the stages.  blob:
+ * wires_cap | zs_partial_products_cap | quotient_cap (2^h x 4 each) | OpeningSet as (a, b) pairs: constants,
+ * plonk_sigmas, wires, plonk_zs, plonk_zs_next, partial_products, quotient_polys | FriProof (eng_fri_prove_openings).
+ * stage_ms (may be NULL, 8 floats): wires commitment, partial products, Z commit, quotient (values + iNTT), quotient
+ * commit, opening set, opening proofs (FRI), total. */
+eng_status eng_prove(const eng_circuit *c, const uint64_t *const *wire_cols_host, const uint64_t *public_inputs_hash,
+                     uint64_t **blob_out, size_t *blob_len, float *stage_ms);
+
+/* Synthetic circuit (tests / bench input generator, host code): 2^degree_bits rows of the five core gates with a
+ * satisfying witness and non-trivial copy constraints.  Caller-allocated outputs, column-major: constants [4][n]
+ * (selector 0, selector 1, gate constants 0 and 1), sigmas [80][n], wires [135][n], pi_hash [4], circuit_blob [36]. */
+eng_status eng_synth_circuit(uint32_t degree_bits, uint64_t seed, uint64_t *constants, uint64_t *sigmas, uint64_t *wires,
+                             uint64_t *pi_hash, uint64_t *circuit_blob);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@
 #include "commit.h"
 #include "challenger.h"
 #include "fri.h"
+#include "plonk.h"
 
 double orc_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -138,6 +139,47 @@ int orc_fri_verify_c(const u64 *instance, const u64 *openings, const u64 *caps, 
 void orc_challenger_state(void *c, u64 *out /* 12 state + 1 n_in + 8 in + 1 n_out + 8 out */) {
     OrcChallenger *ch = (OrcChallenger *)c;
     memcpy(out, ch->state, 96); out[12] = ch->n_in; memcpy(out + 13, ch->in_buf, 64); out[21] = ch->n_out; memcpy(out + 22, ch->out_buf, 64);
+}
+
+
+/* ---- plonk rows (a5, a6) and the whole prove / verify ----
+ * circuit blob: [degree_bits, num_wires, num_routed, num_gate_constants, num_selectors, num_challenges,
+ *   quotient_degree_factor, rate_bits, cap_height, pow_bits, num_query_rounds, num_gates,
+ *   (kind, selector_index, group_start, group_end) x num_gates, circuit_digest x 4] */
+void *orc_circuit_new(const u64 *b) {
+    OrcCircuit *c = new OrcCircuit();
+    c->degree_bits = (int)b[0]; c->num_wires = (int)b[1]; c->num_routed = (int)b[2]; c->num_gate_constants = (int)b[3];
+    c->num_selectors = (int)b[4]; c->num_challenges = (int)b[5]; c->quotient_degree_factor = (int)b[6]; c->rate_bits = (int)b[7];
+    c->cap_height = (int)b[8]; c->pow_bits = (int)b[9]; c->num_query_rounds = (int)b[10];
+    int ng = (int)b[11];
+    for (int i = 0; i < ng; i++) { OrcGateInfo g = {(int)b[12 + 4 * i], (int)b[13 + 4 * i], (int)b[14 + 4 * i], (int)b[15 + 4 * i]}; c->gates.push_back(g); }
+    for (int i = 0; i < 4; i++) c->circuit_digest[i] = gl_canon(b[12 + 4 * ng + i]);
+    u64 k = 1;
+    for (int j = 0; j < c->num_routed; j++) { c->k_is.push_back(k); k = gl_mul(k, GL_GENERATOR); }
+    return c;
+}
+void orc_circuit_free(void *c) { delete (OrcCircuit *)c; }
+void orc_partial_products_c(void *c, const u64 *wires, const u64 *sigmas, const u64 *betas, const u64 *gammas, u64 *out) {
+    vec64 r = orc_partial_products(*(OrcCircuit *)c, wires, sigmas, betas, gammas);
+    memcpy(out, r.data(), r.size() * 8);
+}
+int orc_quotient_c(void *c, void *cs, void *wires, void *zs_pp, const u64 *pi_hash, const u64 *betas, const u64 *gammas, const u64 *alphas, u64 *out) {
+    vec64 r = orc_quotient_polys(*(OrcCircuit *)c, *(OrcBatch *)cs, *(OrcBatch *)wires, *(OrcBatch *)zs_pp, pi_hash, betas, gammas, alphas);
+    if (r.empty()) return 1;
+    memcpy(out, r.data(), r.size() * 8);
+    return 0;
+}
+void *orc_prove_c(void *c, void *cs, const u64 *wire_values, const u64 *sigma_values, const u64 *pi_hash) {
+    OrcProof p;
+    if (!orc_prove(*(OrcCircuit *)c, *(OrcBatch *)cs, wire_values, sigma_values, pi_hash, p)) return nullptr;
+    return new vec64(orc_proof_blob(p));
+}
+int orc_verify_c(void *c, const u64 *cs_cap, const u64 *pi_hash, const u64 *blob, size_t len) {
+    OrcCircuit *C = (OrcCircuit *)c;
+    OrcProof p;
+    if (!orc_proof_from_blob(*C, blob, len, p)) return 100;
+    vec64 cap(cs_cap, cs_cap + ((size_t)4 << C->cap_height));
+    return orc_verify(*C, cap, pi_hash, p);
 }
 
 } /* extern "C" */

@@ -69,6 +69,13 @@ def lib():
         L.orc_fri_verify_c.restype = C.c_int
         L.orc_fri_verify_c.argtypes = [_u64p, _u64p, _u64p, C.POINTER(C.c_int), C.c_int, _u64p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]
         L.orc_challenger_state.argtypes = [C.c_void_p, _u64p]
+        L.orc_circuit_new.restype = C.c_void_p; L.orc_circuit_new.argtypes = [_u64p]
+        L.orc_circuit_free.argtypes = [C.c_void_p]
+        L.orc_partial_products_c.argtypes = [C.c_void_p, _u64p, _u64p, _u64p, _u64p, _u64p]
+        L.orc_quotient_c.restype = C.c_int
+        L.orc_quotient_c.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _u64p, _u64p, _u64p, _u64p, _u64p]
+        L.orc_prove_c.restype = C.c_void_p; L.orc_prove_c.argtypes = [C.c_void_p, C.c_void_p, _u64p, _u64p, _u64p]
+        L.orc_verify_c.restype = C.c_int; L.orc_verify_c.argtypes = [C.c_void_p, _u64p, _u64p, _u64p, C.c_size_t]
         _lib = L
     return _lib
 
@@ -260,6 +267,49 @@ def fri_verify(instance_blob, openings, caps, leaf_lens, proof_blob, challenger,
     proof_blob = _a(proof_blob)
     return lib().orc_fri_verify_c(_a(instance_blob), _a(openings).ravel(), _a(caps).ravel(), ll, len(leaf_lens), proof_blob,
                                   proof_blob.size, challenger.h, params)
+
+
+class Circuit:
+    """Circuit description for the plonk rows (oracle/plonk.h); `blob` layout documented at orc_circuit_new."""
+
+    def __init__(self, blob):
+        self.blob = _a(blob)
+        self.h = lib().orc_circuit_new(self.blob)
+        b = [int(x) for x in self.blob]
+        (self.degree_bits, self.num_wires, self.num_routed, self.num_gate_constants, self.num_selectors, self.num_challenges,
+         self.quotient_degree_factor, self.rate_bits, self.cap_height) = b[:9]
+        self.num_pp = (self.num_routed + self.quotient_degree_factor - 1) // self.quotient_degree_factor - 1
+
+    def partial_products(self, wires, sigmas, betas, gammas):
+        n = 1 << self.degree_bits
+        out = np.zeros((self.num_challenges * (1 + self.num_pp), n), np.uint64)
+        lib().orc_partial_products_c(self.h, _a(wires), _a(sigmas), _a(betas), _a(gammas), out)
+        return out
+
+    def quotient(self, cs, wires, zs_pp, pi_hash, betas, gammas, alphas):
+        n = 1 << self.degree_bits
+        out = np.zeros((self.num_challenges * self.quotient_degree_factor, n), np.uint64)
+        rc = lib().orc_quotient_c(self.h, cs.h, wires.h, zs_pp.h, _a(pi_hash), _a(betas), _a(gammas), _a(alphas), out)
+        if rc:
+            raise ValueError("oracle: quotient_degree_bits != rate_bits is not restated")
+        return out
+
+    def prove(self, cs, wire_values, sigma_values, pi_hash):
+        b = lib().orc_prove_c(self.h, cs.h, _a(wire_values), _a(sigma_values), _a(pi_hash))
+        if not b:
+            raise ValueError("oracle: prove failed")
+        n = lib().orc_blob_len(b)
+        out = np.ctypeslib.as_array(lib().orc_blob_data(b), shape=(n,)).copy()
+        lib().orc_blob_free(b)
+        return out
+
+    def verify(self, cs_cap, pi_hash, proof_blob):
+        proof_blob = _a(proof_blob)
+        return lib().orc_verify_c(self.h, _a(cs_cap).ravel(), _a(pi_hash), proof_blob, proof_blob.size)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_circuit_free(self.h); self.h = None
 
 
 def splitmix_columns(C_, n, seed=0x9E3779B97F4A7C15):

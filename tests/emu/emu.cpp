@@ -13,6 +13,7 @@
 #include "../../eth-lc-plonky2_b200/csrc/merkle.cuh"
 #include "../../eth-lc-plonky2_b200/csrc/ntt.cuh"
 #include "../../eth-lc-plonky2_b200/csrc/ntt_plan.h"
+#include "../../eth-lc-plonky2_b200/csrc/plonk.cuh"
 
 static std::vector<std::unique_ptr<std::vector<u64>>> g_tables;
 
@@ -131,5 +132,61 @@ int emu_plan(u32 C, u32 log_n, u32 rate_bits, int intt, u64 *out, int max) {
         o[0] = l.mode; o[1] = l.p.log_p; o[2] = l.p.log_a; o[3] = l.threads; o[4] = l.smem; o[5] = l.p.num_tiles;
     }
     return k;
+}
+
+// ---- plonk rows: replay of quot_point / pp_row / pp_finish (kernel bodies) on host arrays ----
+static void emu_fill_circuit(const u64 *b, PlkCircuit &C) {
+    C.degree_bits = (u32)b[0]; C.num_wires = (u32)b[1]; C.num_routed = (u32)b[2]; C.num_gate_constants = (u32)b[3];
+    C.num_selectors = (u32)b[4]; C.num_challenges = (u32)b[5]; C.quotient_degree_factor = (u32)b[6]; C.num_gates = (u32)b[11];
+    for (u32 i = 0; i < C.num_gates; i++) {
+        C.gates[i].kind = (u32)b[12 + 4 * i]; C.gates[i].selector_index = (u32)b[13 + 4 * i];
+        C.gates[i].group_start = (u32)b[14 + 4 * i]; C.gates[i].group_end = (u32)b[15 + 4 * i];
+    }
+}
+// LDEs are [cols][L] column-major in bit-reversed row order (the engine's layout); out: [num_challenges][L] natural order
+void emu_quotient_values(const u64 *blob, const u64 *cs_lde, const u64 *wires_lde, const u64 *zs_lde, const u64 *pi_hash,
+                         const u64 *betas, const u64 *gammas, const u64 *alphas, u64 *out) {
+    NttTableStore ts = make_store();
+    QuotParams q;
+    memset(&q, 0, sizeof(q));
+    emu_fill_circuit(blob, q.C);
+    q.log_l = q.C.degree_bits + 3;
+    const u64 n = (u64)1 << q.C.degree_bits, L = n << 3;
+    q.cs = cs_lde; q.wires = wires_lde; q.zs = zs_lde; q.out = out;
+    q.k_is[0] = 1;
+    for (int j = 1; j < 80; j++) q.k_is[j] = h_gl_mul(q.k_is[j - 1], 7);
+    for (u32 i = 0; i < q.C.num_challenges; i++) { q.beta[i] = betas[i]; q.gamma[i] = gammas[i]; q.alpha[i] = alphas[i]; }
+    for (int i = 0; i < 4; i++) q.pi_hash[i] = pi_hash[i];
+    const u64 g_pow_n = h_gl_pow(7, n), w8 = h_gl_root_of_unity(3);
+    for (int i = 0; i < 8; i++) { q.zh[i] = gl_canon(gl_sub(h_gl_mul(g_pow_n, h_gl_pow(w8, i)), 1)); q.zh_inv[i] = h_gl_inv(q.zh[i]); }
+    q.n_field = n % GL_P;
+    auto w = ts.w2((int)q.log_l, false);
+    q.w_lo = w.lo; q.w_hi = w.hi; q.w_lo_bits = w.lo_bits;
+    for (u64 pos = 0; pos < L; pos++) quot_point(q, pos);
+    g_tables.clear();
+}
+void emu_partial_products(const u64 *blob, const u64 *wires, const u64 *sigmas, const u64 *betas, const u64 *gammas, u64 *out) {
+    NttTableStore ts = make_store();
+    PlkCircuit C;
+    memset(&C, 0, sizeof(C));
+    emu_fill_circuit(blob, C);
+    PpParams p;
+    memset(&p, 0, sizeof(p));
+    p.log_n = C.degree_bits; p.num_routed = C.num_routed; p.num_challenges = C.num_challenges; p.degree = C.quotient_degree_factor;
+    const u64 n = (u64)1 << C.degree_bits;
+    std::vector<u64> row_prod((size_t)C.num_challenges * n);
+    p.wires = wires; p.sigmas = sigmas; p.out = out; p.row_prod = row_prod.data();
+    p.k_is[0] = 1;
+    for (int j = 1; j < 80; j++) p.k_is[j] = h_gl_mul(p.k_is[j - 1], 7);
+    for (u32 i = 0; i < C.num_challenges; i++) { p.beta[i] = betas[i]; p.gamma[i] = gammas[i]; }
+    auto w = ts.w2((int)C.degree_bits, false);
+    p.w_lo = w.lo; p.w_hi = w.hi; p.w_lo_bits = w.lo_bits;
+    for (u64 i = 0; i < n; i++) pp_row(p, i);
+    for (u32 c = 0; c < C.num_challenges; c++) {   // the exclusive scan the three scan kernels perform
+        u64 acc = 1;
+        for (u64 i = 0; i < n; i++) { out[(u64)c * n + i] = gl_canon(acc); acc = gl_mul(acc, row_prod[(u64)c * n + i]); }
+    }
+    for (u64 i = 0; i < n; i++) pp_finish(p, i);
+    g_tables.clear();
 }
 }
