@@ -133,7 +133,65 @@ GL_HD u64 acc160_reduce(const acc160 &acc) {
         s[r] = ((u64)v1 << 32) | v0;                                                                             \
     }
 #endif
+// MDS on the FP64 pipe (B200 keeps a full-rate fp64 pipe -- 64 DFMA/clk/SM -- that is otherwise idle in this
+// kernel, while the integer alu and fma pipes are the bottleneck; profiles/r01_pipe_model.md).  All products and sums
+// of the MDS layer are < 2^42, hence exact in binary64: halves enter as 2^52 + x (bit pattern 0x43300000:x) minus
+// 2^52, 2 x 144 DFMA accumulate them, and the sums leave through the mantissa of (sum + 2^52).  Same integers as the
+// IMAD.WIDE formulation; fp addition is not re-associated by the compiler, so this is also free of the un-fusing ptxas
+// applies to integer multiply-add chains.
+#ifndef PSD_MDS_FP64
+#define PSD_MDS_FP64 1
+#endif
+#if defined(__CUDA_ARCH__) && PSD_MDS_FP64
+__device__ __forceinline__ void poseidon_mds_fp64(u64 (&s)[12]) {
+    const double two52 = 4503599627370496.0;
+    const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
+    double lo[12], hi[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        lo[i] = __hiloint2double(0x43300000, (int)(u32)s[i]) - two52;
+        hi[i] = __hiloint2double(0x43300000, (int)(u32)(s[i] >> 32)) - two52;
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        double al = lo[r % 12] * C[0], ah = hi[r % 12] * C[0];
+#pragma unroll
+        for (int i = 1; i < 12; i++) {
+            al = fma(lo[(i + r) % 12], C[i], al);
+            ah = fma(hi[(i + r) % 12], C[i], ah);
+        }
+        if (r == 0) {
+            al = fma(lo[0], 8., al);
+            ah = fma(hi[0], 8., ah);
+        }
+        const u64 ual = (u64)__double_as_longlong(al + two52) & 0x000FFFFFFFFFFFFFull;
+        const u64 uah = (u64)__double_as_longlong(ah + two52) & 0x000FFFFFFFFFFFFFull;
+        u32 v0, v1;
+        asm("{\n\t"
+            ".reg .u32 a0, a1, h0, h1, t, k, tt, hh;\n\t"
+            "mov.b64 {a0, a1}, %2;\n\t"
+            "mov.b64 {h0, h1}, %3;\n\t"
+            "add.u32 t, a1, h1;\n\t"
+            "sub.cc.u32 %0, a0, h1;\n\t"
+            "subc.cc.u32 %1, h0, 0;\n\t"
+            "subc.u32 k, 0, 0;\n\t"
+            "add.cc.u32 %1, %1, t;\n\t"
+            "addc.u32 k, k, 0;\n\t"
+            "sub.u32 tt, 0, k;\n\t"
+            "shr.s32 hh, k, 1;\n\t"
+            "add.cc.u32 %0, %0, tt;\n\t"
+            "addc.u32 %1, %1, hh;\n\t"
+            "}"
+            : "=&r"(v0), "=&r"(v1)
+            : "l"(ual), "l"(uah));
+        s[r] = ((u64)v1 << 32) | v0;
+    }
+}
+#endif
 GL_HD void poseidon_mds(u64 (&s)[12]) {
+#if defined(__CUDA_ARCH__) && PSD_MDS_FP64
+    poseidon_mds_fp64(s);
+#else
     u32 lo[12], hi[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
@@ -161,6 +219,7 @@ GL_HD void poseidon_mds(u64 (&s)[12]) {
         u64 t = l + (u64)top * GL_EPS;
         s[r] = t + (t < l ? (u64)GL_EPS : 0);
     }
+#endif
 #endif
 }
 

@@ -78,16 +78,16 @@ def test_commit_replay_matches_oracle(emu, oracle, C_, log_n, r, h, is_values):
     assert (b.cap == cap).all()
 
 
-@pytest.mark.parametrize("log_n", range(0, 25))
+@pytest.mark.parametrize("log_n", range(0, 27))
 def test_planner_shapes(emu, log_n):
     out = np.zeros(6 * 4, np.uint64)
     for intt in (0, 1):
         k = emu.emu_plan(135, log_n, 3, intt, out, 4)
-        assert k == (1 if log_n <= 12 else 2)
+        assert k == (1 if log_n <= 13 else 2)
         for mode, log_p, log_a, threads, smem, tiles in out.reshape(4, 6)[:k]:
-            assert log_p <= 12 and threads in range(32, 513) and smem <= 200 * 1024 and tiles > 0
-            if mode in (0, 3, 4):                  # strided passes: at least 32-byte segments
-                assert log_a >= 2
+            assert log_p <= 13 and threads in range(32, 513) and smem <= 200 * 1024 and tiles > 0
+            if mode in (0, 3, 4):                  # strided passes: at least 32-byte segments (16 for 2^13-point tiles)
+                assert log_a >= (1 if log_p == 13 else 2)
 
 
 @pytest.mark.parametrize("C_,log_n,r,log_g", [(5, 4, 3, 1), (5, 4, 3, 3), (3, 13, 3, 3), (3, 13, 3, 2), (2, 13, 1, 3), (7, 6, 2, 3)])
