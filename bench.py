@@ -138,6 +138,30 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def proof_section(E, log_n, reps=3):
+    """BASELINE.json's first metric: proof wall-time (s).  The real eth-lc circuit cannot be built here (it needs
+    plonky2's Rust front-end), so this is the circuit-SHAPED synthetic proof of SURVEY.md 8(d): 135 wires, 80 routed,
+    84 constants||sigmas columns, the five core gates (half the rows are PoseidonGate), standard_recursion_config
+    (rate_bits 3, cap_height 4, 16-bit grind, 28 queries), witness on the host, everything after witness generation on
+    the GPU through eng_prove.  Wall clock around the call with host wire columns (H2D inside)."""
+    s = E.synth_circuit(log_n, seed=1)
+    t0 = time.perf_counter()
+    circ = E.Circuit.build(s)
+    E.synchronize()
+    build_s = time.perf_counter() - t0
+    wires = list(s["wires"])
+    walls, stages = [], {}
+    for _ in range(reps):
+        t = time.perf_counter()
+        proof, stages = circ.prove(wires, s["pi_hash"])
+        walls.append(time.perf_counter() - t)
+    return {"metric": "synthetic_proof_wall_time", "value": min(walls[1:]) if len(walls) > 1 else walls[0], "unit": "s",
+            "higher_is_better": False, "log_rows": log_n,
+            "config": "circuit-shaped synthetic proof, 2^%d rows x 135 wires, 5 core gates, standard_recursion_config" % log_n,
+            "build_constants_sigmas_commit_s": build_s, "stage_ms": stages, "proof_u64_words": int(proof.size),
+            "reference_published": "~300 s for the real 2^22-row circuit on 32 vCPU (README.md:71); not comparable 1:1"}
+
+
 def workload_config(cols, log_n, gpus):
     return {"workload": "PolynomialBatch::from_values commit, %d Goldilocks columns x 2^%d rows, rate_bits=3, cap_height=4 "
                         "(BASELINE.json configs[1])" % (cols, log_n),
@@ -156,6 +180,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--cols", type=int, default=135)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--proof-log-n", type=int, default=20, help="rows (log2) of the synthetic circuit-shaped proof; 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -302,6 +327,8 @@ def main():
             "clocks": clocks,
             "cap0": "%016x" % int(cap_e2e[0][0]),
         }
+        if args.proof_log_n:
+            line["proof"] = proof_section(E, args.proof_log_n)
         if not args.no_cpu_baseline and world == 1:
             k = cpu_sample_log_n(cols)
             dt, cpu_stages, threads = cpu_commit(cols, k)

@@ -29,23 +29,28 @@ typedef unsigned __int128 u128;
 
 static inline u64 gl_canon(u64 x) { return x >= GL_P ? x - GL_P : x; }
 
-static inline u64 gl_add(u64 a, u64 b) { /* canonical in, canonical out */
+static inline u64 gl_add(u64 a, u64 b) { /* canonical in, canonical out; branch-free (the carry is a coin flip) */
     u64 s = a + b;
-    if (s < a || s >= GL_P) s -= GL_P;
-    return s;
+    u64 m = 0 - (u64)((s < a) | (s >= GL_P));
+    return s - (GL_P & m);
 }
-static inline u64 gl_sub(u64 a, u64 b) { return a >= b ? a - b : a + (GL_P - b); }
+static inline u64 gl_sub(u64 a, u64 b) {
+    u64 d = a - b;
+    return d + (GL_P & (0 - (u64)(a < b)));
+}
 static inline u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
 
 /* x = lo + hi*2^64, hi = hh*2^32 + hl:  2^64 = eps, 2^96 = -1  =>  x = lo - hh + hl*eps  (A.1) */
 static inline u64 gl_reduce128(u128 x) {
     u64 lo = (u64)x, hi = (u64)(x >> 64);
     u64 hh = hi >> 32, hl = hi & GL_EPS;
-    u64 t0 = lo - hh;
-    if (lo < hh) t0 -= GL_EPS;                  /* borrow: +p  == -eps mod 2^64 */
+    u64 t0;
+    u64 borrow = __builtin_sub_overflow(lo, hh, &t0);
+    t0 -= (0 - borrow) & GL_EPS;                /* borrow: +p  == -eps mod 2^64 */
     u64 t1 = hl * GL_EPS;                       /* < 2^64 */
-    u64 t2 = t0 + t1;
-    if (t2 < t1) t2 += GL_EPS;                  /* carry: -p == +eps mod 2^64 */
+    u64 t2;
+    u64 carry = __builtin_add_overflow(t0, t1, &t2);
+    t2 += (0 - carry) & GL_EPS;                 /* carry: -p == +eps mod 2^64 */
     return gl_canon(t2);
 }
 static inline u64 gl_mul(u64 a, u64 b) { return gl_reduce128((u128)a * b); }

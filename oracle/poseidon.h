@@ -20,12 +20,14 @@ static inline u64 orc_sbox7(u64 x) {
 
 /* out[r] = sum_i in[(i+r)%12]*CIRC[i] + in[r]*DIAG[r]   [poseidon.rs::mds_layer] */
 static inline void orc_mds(u64 s[12]) {
-    u64 o[12];
+    /* on 32-bit halves, as plonky2's mds_row_shf does: every sum is < 2^42, no reduction inside */
+    u64 lo[24], hi[24], o[12];
+    for (int i = 0; i < 12; i++) { lo[i] = lo[i + 12] = s[i] & GL_EPS; hi[i] = hi[i + 12] = s[i] >> 32; }
     for (int r = 0; r < 12; r++) {
-        u128 acc = 0;
-        for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * ORC_MDS_CIRC[i];
-        if (r == 0) acc += (u128)s[0] * POSEIDON_MDS_DIAG0;
-        o[r] = gl_reduce128(acc);
+        u64 al = 0, ah = 0;
+        for (int i = 0; i < 12; i++) { al += lo[i + r] * ORC_MDS_CIRC[i]; ah += hi[i + r] * ORC_MDS_CIRC[i]; }
+        if (r == 0) { al += lo[0] * POSEIDON_MDS_DIAG0; ah += hi[0] * POSEIDON_MDS_DIAG0; }
+        o[r] = gl_reduce128((u128)al + ((u128)ah << 32));
     }
     for (int r = 0; r < 12; r++) s[r] = o[r];
 }
