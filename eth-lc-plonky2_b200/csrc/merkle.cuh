@@ -79,11 +79,11 @@ GL_HD void merkle_hash_node(const MerkleParams &p, u32 layer, u64 g) {
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(128) merkle_leaves_kernel(MerkleParams p) {
+__global__ void __launch_bounds__(128, 4) merkle_leaves_kernel(MerkleParams p) {
     u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < p.num_leaves) merkle_hash_leaf(p, j);
 }
-__global__ void __launch_bounds__(128) merkle_level_kernel(MerkleParams p, u32 layer) {
+__global__ void __launch_bounds__(128, 4) merkle_level_kernel(MerkleParams p, u32 layer) {
     u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g < (p.num_leaves >> (layer + 1))) merkle_hash_node(p, layer, g);
 }

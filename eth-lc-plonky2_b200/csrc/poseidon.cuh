@@ -45,6 +45,9 @@ __constant__ u32 c_mds[13] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20, 8};
 #define PSD_UNROLL1
 #endif
 
+#define POSEIDON_RC_AT(i) PSD_RC(i)
+#include "poseidon_f64.cuh"
+
 #ifdef __CUDACC__
 // Uploads the constant tables of this translation unit; call once per module before the first launch.
 static inline cudaError_t poseidon_upload_constants() {
@@ -54,7 +57,8 @@ static inline cudaError_t poseidon_upload_constants() {
     if ((e = cudaMemcpyToSymbol(c_fast_k, POSEIDON_FAST_K, sizeof(POSEIDON_FAST_K))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_fast_row, POSEIDON_FAST_ROW, sizeof(POSEIDON_FAST_ROW))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_fast_col, POSEIDON_FAST_COL, sizeof(POSEIDON_FAST_COL))) != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_fast_init, POSEIDON_FAST_INIT, sizeof(POSEIDON_FAST_INIT));
+    if ((e = cudaMemcpyToSymbol(c_fast_init, POSEIDON_FAST_INIT, sizeof(POSEIDON_FAST_INIT))) != cudaSuccess) return e;
+    return psd_f64_upload_tables();
 }
 #endif
 
@@ -286,14 +290,27 @@ GL_HD void poseidon_partial_rounds(u64 (&s)[12]) {
     }
 }
 
-// The permutation.  Accepts non-canonical lanes; outputs are exact residues, not necessarily canonical.
-GL_HD void poseidon_permute(u64 (&s)[12]) {
+// The permutation on the integer pipes only (host replay, and the A/B baseline of the FP64 formulation).
+GL_HD void poseidon_permute_int(u64 (&s)[12]) {
     PSD_UNROLL1
     for (int r = 0; r < 8; r++) {
         if (r == 4) poseidon_partial_rounds(s);
         poseidon_full_sbox(s, 12 * (r < 4 ? r : r + 22));
         poseidon_mds(s);
     }
+}
+
+#ifndef PSD_F64
+#define PSD_F64 1
+#endif
+// The permutation.  Accepts non-canonical lanes; outputs are exact residues, not necessarily canonical.
+// Device: linear layers on the FP64 pipe (poseidon_f64.cuh); the integer-only form is kept for the CPU replay harness.
+GL_HD void poseidon_permute(u64 (&s)[12]) {
+#if defined(__CUDA_ARCH__) && PSD_F64
+    poseidon_permute_f64(s);
+#else
+    poseidon_permute_int(s);
+#endif
 }
 
 // two_to_one(l, r) = permute([l, r, 0, 0, 0, 0])[0..4]

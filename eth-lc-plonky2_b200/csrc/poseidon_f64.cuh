@@ -1,0 +1,349 @@
+// Poseidon permutation with every LINEAR layer on the FP64 pipe (exact integer arithmetic below 2^53).
+//
+// Same function as plonky2::hash::poseidon::Poseidon::poseidon for GoldilocksField (dep plonky2 0.1.4,
+// /root/reference/Cargo.lock:2347-2350): 4 full + 22 partial + 4 full rounds of
+//     state += RC_t;  S-box (x^7) on all lanes / on lane 0;  state = MDS * state.
+//
+// Why (profiles/r01_pipe_model.md, profiles/r01_leaves_v1.md): on sm_100a the integer alu pipe is half rate and is
+// what bounds a Poseidon kernel written on the integer pipes (the "fast" partial rounds of plonky2 are 23 full
+// 64x64 products with 64-bit constants per round: 852 alu/fma issue cycles per round per warp).  B200 keeps a
+// 64-lane/clk/SM FP64 pipe that such a kernel leaves idle.  Here
+//   * a lane is carried as a pair of doubles (lo, hi) meaning lo + 2^32*hi (mod p), both signed integers < 2^51;
+//   * the S-box runs on the integer pipes (3 reduced products + 1 unreduced 128-bit product x0..x3), and the final
+//     reduction 2^64 = 2^32 - 1, 2^96 = -1 happens in FP64:  lo = x0 - x2 - x3,  hi = x1 + x2;
+//   * the MDS layer (coefficients <= 41) is 2 x 145 DFMA per layer; the NEXT round's constants are the initial
+//     values of the accumulation chains, so adding round constants costs nothing;
+//   * the 22 partial rounds run in their NAIVE form, two rounds per step: with W = state after the first S-box,
+//         b  = (M W + RC_{t+1})[0],   b' = b^7,
+//         state_{t+2} = M^2 W + (M RC_{t+1} + RC_{t+2}) + (b' - b) * M e_0
+//     (M^2 has entries < 2^15, so 2^32 * 264^2 < 2^49 stays exact).  Lanes 1..11 never leave the FP64 domain during
+//     the partial rounds; they are re-normalised to |lo|,|hi| <= 2^31 + 2^19 with 9 FP64 operations every two rounds.
+//     Only lane 0 crosses to the integer side (one fold per round) for its S-box;
+//   * a pair (al, ah) is folded back to a u64 through the mantissa of al + 1.5*2^52 (a bias of 2^51 on both halves,
+//     compensated inside the chain-init constants), then one 10-instruction carry chain.
+//
+// Everything is exact: the result is bit-identical to the integer formulation (tests: upstream KATs, oracle parity).
+// The file is __host__ __device__ so that tests/emu replays the same arithmetic on the CPU of the GPU-less
+// development container (IEEE binary64 with fma is the same arithmetic on both sides).
+#pragma once
+#include "gl64.cuh"
+#include "poseidon_consts.h"
+#include <math.h>
+#include <string.h>
+
+struct PsdF64Tables {
+    double full_init[8][12][2];  // chain-init constants of the 8 full-round MDS layers [layer][lane][lo, hi]
+    double pair_t0[11][2];       // RC_{t+1}[0] - B
+    double pair_k[11][12][2];    // M RC_{t+1} + RC_{t+2} - B * M e_0 (- B where the lane is folded next)
+    double m2[12][12];           // M^2
+    double m_row0[12];           // M[0][j]
+    double m_col0[12];           // M[r][0]
+    double circ[12];             // MDS_MATRIX_CIRC
+};
+
+#ifdef __CUDACC__
+__constant__ PsdF64Tables c_pf;
+#endif
+#ifdef __CUDA_ARCH__
+#define PF_T(x) c_pf.x
+#else
+static PsdF64Tables h_pf;
+#define PF_T(x) h_pf.x
+#endif
+
+#define PF_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
+#define PF_BIAS 0x000FFFFFFFF80000ULL /* B = 2^51 + 2^83 = 2^52 - 2^19 (mod p): what a fold adds to the value */
+
+// ---- host: table construction (exact field arithmetic) ----
+static inline void psd_f64_build_tables(PsdF64Tables &t) {
+    const u64 circ[12] = POSEIDON_MDS_CIRC_INIT;
+    u64 M[12][12];
+    memset(M, 0, sizeof(M));
+    for (int r = 0; r < 12; r++)
+        for (int i = 0; i < 12; i++) M[r][(i + r) % 12] += circ[i];
+    M[0][0] += POSEIDON_MDS_DIAG0;
+    for (int r = 0; r < 12; r++)
+        for (int j = 0; j < 12; j++) {
+            u64 a = 0;
+            for (int k = 0; k < 12; k++) a += M[r][k] * M[k][j];
+            t.m2[r][j] = (double)a;
+        }
+    for (int j = 0; j < 12; j++) {
+        t.m_row0[j] = (double)M[0][j];
+        t.m_col0[j] = (double)M[j][0];
+        t.circ[j] = (double)circ[j];
+    }
+    auto sub = [](u64 a, u64 b) { return a >= b ? a - b : a + (GL_P - b); };   // canonical a, b
+    auto add = [](u64 a, u64 b) { u64 s = a + b; return (s < a || s >= GL_P) ? s - GL_P : s; };
+    auto put = [](double (&d)[2], u64 v) { d[0] = (double)(u32)v; d[1] = (double)(u32)(v >> 32); };
+    auto rc = [](int round, int lane) -> u64 { return round < 30 ? POSEIDON_RC[12 * round + lane] % GL_P : 0; };
+    const u64 B = PF_BIAS;
+    for (int L = 0; L < 8; L++) {
+        int next_round = L < 4 ? L + 1 : 27 + (L - 4);   // constants of the round that follows the layer
+        for (int j = 0; j < 12; j++) put(t.full_init[L][j], sub(rc(next_round, j), B));
+    }
+    for (int p = 0; p < 11; p++) {
+        int r1 = 4 + 2 * p + 1, r2 = r1 + 1;
+        put(t.pair_t0[p], sub(rc(r1, 0), B));
+        for (int r = 0; r < 12; r++) {
+            u64 k = rc(r2, r);
+            for (int j = 0; j < 12; j++) k = add(k, h_gl_mul(M[r][j], rc(r1, j)));
+            k = sub(k, h_gl_mul(B, M[r][0]));
+            if (r == 0 || p == 10) k = sub(k, B);
+            put(t.pair_k[p][r], k);
+        }
+    }
+}
+
+#ifdef __CUDACC__
+static inline cudaError_t psd_f64_upload_tables() {
+    PsdF64Tables t;
+    psd_f64_build_tables(t);
+    return cudaMemcpyToSymbol(c_pf, &t, sizeof(t));
+}
+#endif
+
+// ---- primitives ----
+#ifndef PF_CVT_MAGIC
+#define PF_CVT_MAGIC 0   // 0: I2F.F64.U32 on the conversion unit; 1: 2^52-mantissa trick (one more DADD, two moves)
+#endif
+GL_HD double pf_cvt(u32 w) {
+#if defined(__CUDA_ARCH__) && PF_CVT_MAGIC
+    return __hiloint2double(0x43300000, (int)w) - 4503599627370496.0;
+#else
+    return (double)w;
+#endif
+}
+GL_HD double pf_fma(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+    return fma(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+GL_HD u64 pf_bits(double x) {
+#ifdef __CUDA_ARCH__
+    return (u64)__double_as_longlong(x);
+#else
+    u64 u;
+    memcpy(&u, &x, 8);
+    return u;
+#endif
+}
+
+// (al, ah), both in (-2^51, 2^51)  ->  some u64 = (al + 2^51) + 2^32 * (ah + 2^51)  (mod p).
+// With ua = a0 + 2^32 a1, uh = h0 + 2^32 h1 (a1, h1 < 2^20):  value = (a0 - h1) + 2^32 * (a1 + h0 + h1).
+GL_HD u64 pf_fold(double al, double ah) {
+    const u64 ua = pf_bits(al + PF_MAGIC), uh = pf_bits(ah + PF_MAGIC);   // mantissa = x + 2^51
+#ifdef __CUDA_ARCH__
+    u32 v0, v1;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, h0, h1, t, k, tt, hh;\n\t"
+        "mov.b64 {a0, a1}, %2;\n\t"
+        "mov.b64 {h0, h1}, %3;\n\t"
+        "and.b32 a1, a1, 0xFFFFF;\n\t"
+        "and.b32 h1, h1, 0xFFFFF;\n\t"
+        "add.u32 t, a1, h1;\n\t"
+        "sub.cc.u32 %0, a0, h1;\n\t"
+        "subc.cc.u32 %1, h0, 0;\n\t"
+        "subc.u32 k, 0, 0;\n\t"
+        "add.cc.u32 %1, %1, t;\n\t"
+        "addc.u32 k, k, 0;\n\t"
+        "sub.u32 tt, 0, k;\n\t"
+        "shr.s32 hh, k, 1;\n\t"
+        "add.cc.u32 %0, %0, tt;\n\t"
+        "addc.u32 %1, %1, hh;\n\t"
+        "}"
+        : "=&r"(v0), "=&r"(v1)
+        : "l"(ua), "l"(uh));
+    return ((u64)v1 << 32) | v0;
+#else
+    const u64 a = ua & 0xFFFFFFFFFFFFFULL, h = uh & 0xFFFFFFFFFFFFFULL;
+    u64 l = a + (h << 32);
+    u64 top = (h >> 32) + (l < a ? 1u : 0u);
+    u64 t = l + top * GL_EPS;
+    return t + (t < l ? (u64)GL_EPS : 0);
+#endif
+}
+
+// re-normalise a pair without changing lo + 2^32 hi (mod p):  |lo|, |hi| < 2^50  ->  |lo| <= 2^31 + 2^18, |hi| <= 2^31 + 2^19
+GL_HD void pf_renorm(double &lo, double &hi) {
+    const double I32 = 1.0 / 4294967296.0, N32 = -4294967296.0;
+    const double a1 = pf_fma(lo, I32, PF_MAGIC) - PF_MAGIC;   // rint(lo / 2^32)
+    const double a0 = pf_fma(a1, N32, lo);
+    const double h1 = pf_fma(hi, I32, PF_MAGIC) - PF_MAGIC;
+    const double h0 = pf_fma(h1, N32, hi);
+    lo = a0 - h1;                                              // 2^64 h1 = 2^32 h1 - h1
+    hi = (a1 + h0) + h1;
+}
+
+// x^7 with the last product left unreduced (x0 + 2^32 x1 + 2^64 x2 + 2^96 x3) and reduced in FP64.
+GL_HD void pf_pow7(u64 x, double &lo, double &hi) {
+    const u64 x2 = gl_sqr(x);
+    const u64 x4 = gl_sqr(x2);
+    const u64 x3 = gl_mul(x, x2);
+    const u64 pl = x3 * x4, ph = gl_mulhi64(x3, x4);
+    const double d0 = pf_cvt((u32)pl), d1 = pf_cvt((u32)(pl >> 32)), d2 = pf_cvt((u32)ph), d3 = pf_cvt((u32)(ph >> 32));
+    lo = (d0 - d2) - d3;
+    hi = d1 + d2;
+}
+
+// out = init + M * in, per half.  M = circ(CIRC) + 8 e0 e0^T.
+// PF_MDS_ORDER 0: row by row (12 chains of 12).  1: column by column -- 12 consecutive DFMAs share the multiplicand
+// register, which the operand-reuse cache serves (a DFMA with three fresh register operands issues every 3 cycles,
+// one with a reused operand every 2.2: tools/bench/pipe_bench2.cu).
+#ifndef PF_MDS_ORDER
+#define PF_MDS_ORDER 1
+#endif
+GL_HD void pf_mds(const double (&xl)[12], const double (&xh)[12], int layer, double (&al)[12], double (&ah)[12]) {
+#if PF_MDS_ORDER == 0
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        double l = PF_T(full_init)[layer][r][0], h = PF_T(full_init)[layer][r][1];
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            l = pf_fma(xl[(i + r) % 12], PF_T(circ)[i], l);
+            h = pf_fma(xh[(i + r) % 12], PF_T(circ)[i], h);
+        }
+        if (r == 0) {
+            l = pf_fma(xl[0], 8.0, l);
+            h = pf_fma(xh[0], 8.0, h);
+        }
+        al[r] = l;
+        ah[r] = h;
+    }
+#else
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        al[r] = PF_T(full_init)[layer][r][0];
+        ah[r] = PF_T(full_init)[layer][r][1];
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+#pragma unroll
+        for (int r = 0; r < 12; r++) al[r] = pf_fma(xl[k], PF_T(circ)[(k - r + 12) % 12], al[r]);
+#pragma unroll
+        for (int r = 0; r < 12; r++) ah[r] = pf_fma(xh[k], PF_T(circ)[(k - r + 12) % 12], ah[r]);
+    }
+    al[0] = pf_fma(xl[0], 8.0, al[0]);
+    ah[0] = pf_fma(xh[0], 8.0, ah[0]);
+#endif
+}
+
+#ifndef PF_SBOX_LANES
+#define PF_SBOX_LANES 6
+#endif
+#ifdef __CUDA_ARCH__
+#define PF_UNROLL1 _Pragma("unroll 1")
+#else
+#define PF_UNROLL1
+#endif
+
+// One full round on an integer state that already holds state + RC_t:  S-box, MDS (+ RC_{t+1} - B), fold.
+GL_HD void pf_full_round(u64 (&s)[12], int layer) {
+    double xl[12], xh[12];
+#if PF_SBOX_LANES == 12
+#pragma unroll
+    for (int k = 0; k < 12; k++) pf_pow7(s[k], xl[k], xh[k]);
+#else
+    // rolled: PF_SBOX_LANES lanes per iteration; s, xl, xh rotate so that every iteration addresses the same registers
+#pragma unroll
+    for (int k = 0; k < 12; k++) xl[k] = xh[k] = 0.0;
+    PF_UNROLL1
+    for (int it = 0; it < 12 / PF_SBOX_LANES; it++) {
+        double tl[PF_SBOX_LANES], th[PF_SBOX_LANES];
+#pragma unroll
+        for (int k = 0; k < PF_SBOX_LANES; k++) pf_pow7(s[k], tl[k], th[k]);
+#pragma unroll
+        for (int k = 0; k < 12 - PF_SBOX_LANES; k++) {
+            s[k] = s[k + PF_SBOX_LANES];
+            xl[k] = xl[k + PF_SBOX_LANES];
+            xh[k] = xh[k + PF_SBOX_LANES];
+        }
+#pragma unroll
+        for (int k = 0; k < PF_SBOX_LANES; k++) {
+            xl[12 - PF_SBOX_LANES + k] = tl[k];
+            xh[12 - PF_SBOX_LANES + k] = th[k];
+        }
+    }
+#endif
+    double al[12], ah[12];
+    pf_mds(xl, xh, layer, al, ah);
+#pragma unroll
+    for (int r = 0; r < 12; r++) s[r] = pf_fold(al[r], ah[r]);
+}
+
+// The 22 partial rounds, two per step.  In: integer state + RC_4.  Out: integer state + RC_26.
+GL_HD void pf_partial_rounds(u64 (&s)[12]) {
+    double al[12], ah[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        al[j] = pf_cvt((u32)s[j]);
+        ah[j] = pf_cvt((u32)(s[j] >> 32));
+    }
+    al[0] -= 2251799813685248.0;   // lane 0 enters every step through a fold (which adds 2^51 to both halves)
+    ah[0] -= 2251799813685248.0;
+    PF_UNROLL1
+    for (int p = 0; p < 11; p++) {
+        const u64 a = pf_fold(al[0], ah[0]);
+#pragma unroll
+        for (int j = 1; j < 12; j++) pf_renorm(al[j], ah[j]);
+        pf_pow7(a, al[0], ah[0]);                       // W
+        double t0l = PF_T(pair_t0)[p][0], t0h = PF_T(pair_t0)[p][1];
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            t0l = pf_fma(al[j], PF_T(m_row0)[j], t0l);
+            t0h = pf_fma(ah[j], PF_T(m_row0)[j], t0h);
+        }
+        const u64 b = pf_fold(t0l, t0h);                // lane 0 entering the second S-box (RC included)
+        double nl[12], nh[12];                          // M^2 W + K: independent of b, overlaps the S-box below
+#if PF_MDS_ORDER == 0
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+            double l = PF_T(pair_k)[p][r][0], h = PF_T(pair_k)[p][r][1];
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                l = pf_fma(al[j], PF_T(m2)[r][j], l);
+                h = pf_fma(ah[j], PF_T(m2)[r][j], h);
+            }
+            nl[r] = l;
+            nh[r] = h;
+        }
+#else
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+            nl[r] = PF_T(pair_k)[p][r][0];
+            nh[r] = PF_T(pair_k)[p][r][1];
+        }
+#pragma unroll
+        for (int jj = 0; jj < 12; jj++) {
+            const int j = (jj + 1) % 12;                // lane 0 (the S-box output) last
+#pragma unroll
+            for (int r = 0; r < 12; r++) nl[r] = pf_fma(al[j], PF_T(m2)[r][j], nl[r]);
+#pragma unroll
+            for (int r = 0; r < 12; r++) nh[r] = pf_fma(ah[j], PF_T(m2)[r][j], nh[r]);
+        }
+#endif
+        double bl, bh;
+        pf_pow7(b, bl, bh);
+        const double dl = bl - t0l, dh = bh - t0h;      // (b' - b) + B as a pair
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+            al[r] = pf_fma(PF_T(m_col0)[r], dl, nl[r]);
+            ah[r] = pf_fma(PF_T(m_col0)[r], dh, nh[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) s[r] = pf_fold(al[r], ah[r]);
+}
+
+// The permutation.  Accepts non-canonical lanes; outputs are exact residues, not necessarily canonical.
+GL_HD void poseidon_permute_f64(u64 (&s)[12]) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], POSEIDON_RC_AT(i));
+    PF_UNROLL1
+    for (int L = 0; L < 8; L++) {
+        if (L == 4) pf_partial_rounds(s);
+        pf_full_round(s, L);
+    }
+}

@@ -190,3 +190,15 @@ void emu_partial_products(const u64 *blob, const u64 *wires, const u64 *sigmas, 
     g_tables.clear();
 }
 }
+
+// the FP64 formulation of the permutation (poseidon_f64.cuh) replayed with host IEEE doubles
+extern "C" void emu_poseidon_permute_f64(const u64 *in, u64 *out, size_t count) {
+    static bool built = false;
+    if (!built) { psd_f64_build_tables(h_pf); built = true; }
+    for (size_t i = 0; i < count; i++) {
+        u64 s[12];
+        for (int k = 0; k < 12; k++) s[k] = in[12 * i + k];
+        poseidon_permute_f64(s);
+        for (int k = 0; k < 12; k++) out[12 * i + k] = gl_canon(s[k]);
+    }
+}

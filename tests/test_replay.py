@@ -26,6 +26,7 @@ def emu():
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
     L = C.CDLL(so)
     L.emu_poseidon_permute.argtypes = [u64p, u64p, C.c_size_t]
+    L.emu_poseidon_permute_f64.argtypes = [u64p, u64p, C.c_size_t]
     L.emu_batch_from_values.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, u64p, u64p, u64p, u64p]
     L.emu_batch_from_values.restype = C.c_int
     L.emu_plan.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u64p, C.c_int]
@@ -53,6 +54,23 @@ def test_poseidon_body(emu, oracle):
     emu.emu_poseidon_permute(st, out, st.shape[0])
     for i in range(st.shape[0]):
         assert (oracle.poseidon(st[i]) == out[i]).all()
+
+
+def test_poseidon_fp64_formulation(emu, oracle):
+    """poseidon_f64.cuh (the device permutation: linear layers in exact binary64, partial rounds two at a time) replayed
+    with host IEEE doubles: the four upstream KATs, edge inputs, and agreement with the integer formulation."""
+    from helpers import golden, unhx
+    rng = np.random.default_rng(7)
+    st = rand_field(rng, (3000, 12), noncanonical=True)
+    st[0] = 0; st[1] = np.arange(12); st[2] = P - 1; st[3] = 2**64 - 1; st[4] = 2**32 - 1; st[5] = 2**64 - 2**32
+    st[6] = np.array([0, 2**64 - 1] * 6, np.uint64); st[7] = P
+    out = np.zeros_like(st); ref = np.zeros_like(st)
+    emu.emu_poseidon_permute_f64(st, out, st.shape[0])
+    emu.emu_poseidon_permute(st, ref, st.shape[0])
+    assert (out == ref).all()
+    for i in range(8):
+        assert (oracle.poseidon(st[i]) == out[i]).all()
+    assert int(out[0][0]) == 0x3C18A9786CB0B359      # upstream KAT, all-zero input
 
 
 CASES = [(3, 0, 1, 0), (3, 1, 1, 1), (5, 2, 2, 0), (9, 3, 1, 1), (3, 3, 3, 2), (135, 4, 3, 4), (7, 5, 3, 2), (9, 7, 2, 3),
