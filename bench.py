@@ -138,7 +138,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def proof_section(E, log_n, reps=3):
+def proof_section(E, log_n, reps=4):
     """BASELINE.json's first metric: proof wall-time (s).  The real eth-lc circuit cannot be built here (it needs
     plonky2's Rust front-end), so this is the circuit-SHAPED synthetic proof of SURVEY.md 8(d): 135 wires, 80 routed,
     84 constants||sigmas columns, the five core gates (half the rows are PoseidonGate), standard_recursion_config
@@ -150,12 +150,16 @@ def proof_section(E, log_n, reps=3):
     E.synchronize()
     build_s = time.perf_counter() - t0
     wires = list(s["wires"])
-    walls, stages = [], {}
-    for _ in range(reps):
+    walls, stages, best = [], {}, None
+    for i in range(reps):
         t = time.perf_counter()
-        proof, stages = circ.prove(wires, s["pi_hash"])
+        proof, st = circ.prove(wires, s["pi_hash"])
         walls.append(time.perf_counter() - t)
-    return {"metric": "synthetic_proof_wall_time", "value": min(walls[1:]) if len(walls) > 1 else walls[0], "unit": "s",
+        if i and (best is None or walls[-1] < best):     # the first call pays table construction and pool growth
+            best, stages = walls[-1], st
+    if best is None:
+        best, stages = walls[0], st
+    return {"metric": "synthetic_proof_wall_time", "value": best, "unit": "s", "all_runs_s": walls,
             "higher_is_better": False, "log_rows": log_n,
             "config": "circuit-shaped synthetic proof, 2^%d rows x 135 wires, 5 core gates, standard_recursion_config" % log_n,
             "build_constants_sigmas_commit_s": build_s, "stage_ms": stages, "proof_u64_words": int(proof.size),

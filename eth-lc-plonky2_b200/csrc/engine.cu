@@ -7,9 +7,11 @@
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/plonky2_b200.h"
@@ -61,6 +63,13 @@ struct Ctx {
     uint64_t launches = 0;
     cudaEvent_t ev[8] = {};
     std::map<std::pair<u64, u32>, NttTableStore::W2> pow_cache;   // two-level power tables of arbitrary bases
+    // host-input pipeline: copies run on copy_stream while the previous column chunk transforms on `stream`
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_ev = nullptr, fork_ev = nullptr;
+    u64 *stage[2] = {nullptr, nullptr};      // pinned bounce buffers for pageable sources
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    size_t stage_elems = 0;
+    int stage_next = 0;
 };
 Ctx g;
 
@@ -214,10 +223,87 @@ void destroy_batch(eng_batch *b) {
     delete b;
 }
 
+
+// ---- host -> device column copies -------------------------------------------------------------------------------------
+// A PolynomialBatch arrives as C host columns (plonky2: Vec<PolynomialValues<F>>).  Page-locked (or registered) columns go
+// straight to the copy engine.  Pageable columns -- what a Rust Vec is -- would make cudaMemcpyAsync a single-threaded
+// bounce copy (~10 GB/s), so they are staged through two pinned buffers by a few host threads and sent from there.
+constexpr size_t STAGE_BYTES = (size_t)64 << 20;
+// test hooks: ENG_H2D_STAGE_BYTES / ENG_H2D_CHUNK_BYTES shrink the bounce buffers / the column chunk so that small
+// parity cases run through several chunks and several bounce-buffer refills
+size_t env_bytes(const char *name, size_t dflt) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    unsigned long long x = strtoull(v, nullptr, 10);
+    return x >= 64 ? (size_t)x : dflt;
+}
+
+bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+eng_status ensure_stage() {
+    const size_t bytes = env_bytes("ENG_H2D_STAGE_BYTES", STAGE_BYTES);
+    if (g.stage[0] && g.stage_elems == bytes / sizeof(u64)) return ENG_OK;
+    for (int i = 0; i < 2; i++) {
+        if (g.stage[i]) { CU(cudaEventSynchronize(g.stage_ev[i])); CU(cudaFreeHost(g.stage[i])); g.stage[i] = nullptr; }
+        if (!g.stage_ev[i]) CU(cudaEventCreateWithFlags(&g.stage_ev[i], cudaEventDisableTiming));
+        CU(cudaHostAlloc((void **)&g.stage[i], bytes, cudaHostAllocDefault));
+    }
+    g.stage_elems = bytes / sizeof(u64);
+    return ENG_OK;
+}
+
+// dst[cc][n] (device, contiguous) <- cols[0..cc) (host), enqueued on g.copy_stream.
+eng_status h2d_columns(const uint64_t *const *cols, uint32_t cc, u64 n, u64 *dst) {
+    bool pinned = true;
+    for (uint32_t c = 0; c < cc && pinned; c++) pinned = host_ptr_is_pinned(cols[c]);
+    if (pinned) {
+        for (uint32_t c = 0; c < cc; c++)
+            CU(cudaMemcpyAsync(dst + (size_t)c * n, cols[c], n * sizeof(u64), cudaMemcpyHostToDevice, g.copy_stream));
+        return ENG_OK;
+    }
+    ST(ensure_stage());
+    const u64 total = (u64)cc * n;
+    unsigned hw = std::thread::hardware_concurrency();
+    const unsigned T = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1);
+    for (u64 s0 = 0; s0 < total; s0 += g.stage_elems) {
+        const u64 len = total - s0 < g.stage_elems ? total - s0 : g.stage_elems;
+        const int slot = g.stage_next;
+        g.stage_next ^= 1;
+        CU(cudaEventSynchronize(g.stage_ev[slot]));      // the previous copy out of this buffer has finished
+        u64 *buf = g.stage[slot];
+        auto work = [&](unsigned t) {                     // flat range [a, b) of the virtual concatenation of the columns
+            u64 a = s0 + len * t / T, b = s0 + len * (t + 1) / T;
+            while (a < b) {
+                u64 c = a / n, off = a % n;
+                u64 run = n - off < b - a ? n - off : b - a;
+                memcpy(buf + (a - s0), cols[c] + off, run * sizeof(u64));
+                a += run;
+            }
+        };
+        if (T == 1 || len < (1u << 16)) {
+            for (unsigned t = 0; t < T; t++) work(t);
+        } else {
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < T; t++) th.emplace_back(work, t);
+            work(0);
+            for (auto &x : th) x.join();
+        }
+        CU(cudaMemcpyAsync(dst + s0, buf, len * sizeof(u64), cudaMemcpyHostToDevice, g.copy_stream));
+        CU(cudaEventRecord(g.stage_ev[slot], g.copy_stream));
+    }
+    return ENG_OK;
+}
+
 // Shared tail of from_values / from_coeffs.  `src` holds values (is_values) or coefficients, either as C host
 // column pointers (cols_host) or as one device array [C][n] (src_dev).
+// values_keep_dev (optional, host input only): receives a device copy [C][n] of the input columns as they arrive.
 eng_status make_batch(const uint64_t *const *cols_host, const u64 *src_dev, bool is_values, uint32_t C, uint32_t log_n,
-                      uint32_t rate_bits, int32_t blinding, uint64_t seed, uint32_t cap_height, eng_batch **out) {
+                      uint32_t rate_bits, int32_t blinding, uint64_t seed, uint32_t cap_height, eng_batch **out,
+                      u64 *values_keep_dev = nullptr) {
     ST(check_ready());
     if (!out) return fail(ENG_ERR_INVALID, "out is NULL");
     *out = nullptr;
@@ -245,32 +331,56 @@ eng_status make_batch(const uint64_t *const *cols_host, const u64 *src_dev, bool
     }
     b->leaf_data = b->lde; b->row_stride = 1; b->col_stride = L;
 
-    auto bail = [&](eng_status s) { destroy_batch(b); return s; };
+    auto bail = [&](eng_status s) { if (g.copy_stream) cudaStreamSynchronize(g.copy_stream); destroy_batch(b); return s; };
 #define STB(call) do { eng_status s__ = (call); if (s__ != ENG_OK) return bail(s__); } while (0)
 #define CUB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(fail(ENG_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__))); } while (0)
 
     CUB(cudaEventRecord(g.ev[0], g.stream));
-    const u64 *src = src_dev;
-    if (cols_host) {
-        for (uint32_t c = 0; c < C; c++) {
-            if (!cols_host[c]) return bail(fail(ENG_ERR_INVALID, "column %u is NULL", c));
-            CUB(cudaMemcpyAsync(b->coeffs + (size_t)c * n, cols_host[c], n * sizeof(u64), cudaMemcpyHostToDevice, g.stream));
-        }
-        src = b->coeffs;
-    }
-    CUB(cudaEventRecord(g.ev[1], g.stream));
     std::vector<NttLaunch> plan;
-    if (is_values) {
-        // iNTT; the (not yet written) LDE buffer is the four-step scratch
-        if (!ntt_plan_intt(g.tables, src, n, b->lde, n, b->coeffs, n, C, log_n, plan)) return bail(fail(ENG_ERR_INVALID, "iNTT size unsupported"));
+    if (cols_host) {
+        // Host columns: pipelined by column chunk.  Chunk k is copied on the copy stream while chunk k-1 runs its iNTT
+        // and coset LDE on the compute stream, so the transfer hides behind the transforms (the leaf hash needs every
+        // column and follows).  The iNTT scratch of a chunk is the LDE region of its own columns, not yet written.
+        for (uint32_t c = 0; c < C; c++)
+            if (!cols_host[c]) return bail(fail(ENG_ERR_INVALID, "column %u is NULL", c));
+        u64 per = env_bytes("ENG_H2D_CHUNK_BYTES", (size_t)32 << 20) / (n * sizeof(u64));
+        const uint32_t chunk = (uint32_t)(per < 1 ? 1 : (per > C ? C : per));
+        CUB(cudaEventRecord(g.fork_ev, g.stream));                 // the buffers were allocated in g.stream's order
+        CUB(cudaStreamWaitEvent(g.copy_stream, g.fork_ev, 0));
+        for (uint32_t c0 = 0; c0 < C; c0 += chunk) {
+            const uint32_t cc = C - c0 < chunk ? C - c0 : chunk;
+            u64 *co = b->coeffs + (size_t)c0 * n, *ld = b->lde + (size_t)c0 * L;
+            STB(h2d_columns(cols_host + c0, cc, n, co));
+            CUB(cudaEventRecord(g.chunk_ev, g.copy_stream));
+            CUB(cudaStreamWaitEvent(g.stream, g.chunk_ev, 0));
+            if (values_keep_dev)
+                CUB(cudaMemcpyAsync(values_keep_dev + (size_t)c0 * n, co, (size_t)cc * n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+            if (is_values) {
+                plan.clear();
+                if (!ntt_plan_intt(g.tables, co, n, ld, n, co, n, cc, log_n, plan)) return bail(fail(ENG_ERR_INVALID, "iNTT size unsupported"));
+                STB(launch_plan(plan));
+            }
+            plan.clear();
+            if (!ntt_plan_lde(g.tables, co, n, ld, cc, log_n, rate_bits, 0, plan)) return bail(fail(ENG_ERR_INVALID, "LDE size unsupported"));
+            STB(launch_plan(plan));
+        }
+        CUB(cudaEventRecord(g.ev[1], g.stream));   // stage_ms: "host to device" = the whole pipelined copy + transforms
+        CUB(cudaEventRecord(g.ev[2], g.stream));
+    } else {
+        const u64 *src = src_dev;
+        CUB(cudaEventRecord(g.ev[1], g.stream));
+        if (is_values) {
+            // iNTT; the (not yet written) LDE buffer is the four-step scratch
+            if (!ntt_plan_intt(g.tables, src, n, b->lde, n, b->coeffs, n, C, log_n, plan)) return bail(fail(ENG_ERR_INVALID, "iNTT size unsupported"));
+            STB(launch_plan(plan));
+        } else if (src != b->coeffs) {
+            CUB(cudaMemcpyAsync(b->coeffs, src, (size_t)C * n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+        }
+        CUB(cudaEventRecord(g.ev[2], g.stream));
+        plan.clear();
+        if (!ntt_plan_lde(g.tables, b->coeffs, n, b->lde, C, log_n, rate_bits, 0, plan)) return bail(fail(ENG_ERR_INVALID, "LDE size unsupported"));
         STB(launch_plan(plan));
-    } else if (src != b->coeffs) {
-        CUB(cudaMemcpyAsync(b->coeffs, src, (size_t)C * n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
     }
-    CUB(cudaEventRecord(g.ev[2], g.stream));
-    plan.clear();
-    if (!ntt_plan_lde(g.tables, b->coeffs, n, b->lde, C, log_n, rate_bits, 0, plan)) return bail(fail(ENG_ERR_INVALID, "LDE size unsupported"));
-    STB(launch_plan(plan));
     if (blinding) {
         u64 count = (u64)SALT_SIZE * L;
         salt_kernel<<<(unsigned)((count + 255) / 256), 256, 0, g.stream>>>(b->lde + (size_t)C * L, count, seed);
@@ -316,6 +426,9 @@ eng_status eng_init(int32_t device) {
     CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
     for (auto &ev : g.ev) CU(cudaEventCreate(&ev));
+    CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&g.chunk_ev, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;
@@ -343,6 +456,15 @@ eng_status eng_shutdown(void) {
     g.tables.tw_local_cache.clear(); g.tables.w2_cache.clear(); g.tables.shift_cache.clear(); g.pow_cache.clear();
     for (auto &ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
     if (g.own_stream) cudaStreamDestroy(g.own_stream);
+    if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
+    if (g.chunk_ev) cudaEventDestroy(g.chunk_ev);
+    if (g.fork_ev) cudaEventDestroy(g.fork_ev);
+    for (int i = 0; i < 2; i++) {
+        if (g.stage[i]) cudaFreeHost(g.stage[i]);
+        if (g.stage_ev[i]) cudaEventDestroy(g.stage_ev[i]);
+        g.stage[i] = nullptr; g.stage_ev[i] = nullptr;
+    }
+    g.copy_stream = nullptr; g.chunk_ev = g.fork_ev = nullptr;
     g.own_stream = g.stream = nullptr;
     g.ready = false;
     return ENG_OK;

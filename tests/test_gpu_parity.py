@@ -106,6 +106,35 @@ def test_device_input_equals_host_input(engine, oracle):
     assert (t.cpu().numpy().view(np.uint64) == vals).all()      # the caller's buffer is not modified
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_input_pipeline_chunks_and_bounce_buffers(engine, oracle, pinned, monkeypatch):
+    """eng_batch_from_values with HOST columns runs as a pipeline: column chunks are copied on a second stream while the
+    previous chunk transforms; pageable columns go through two pinned bounce buffers filled by host threads.  The
+    test hooks shrink the chunk (5 columns) and the bounce buffers (1.3 columns) so that a small case crosses every seam."""
+    import torch
+    C_, log_n = 23, 12
+    n = 1 << log_n
+    monkeypatch.setenv("ENG_H2D_CHUNK_BYTES", str(5 * n * 8))
+    monkeypatch.setenv("ENG_H2D_STAGE_BYTES", str(int(1.3 * n) * 8))
+    vals = oracle.splitmix_columns(C_, n)
+    o = oracle.Batch.from_values(vals, 3, 4)
+    if pinned:
+        t = torch.from_numpy(vals.copy().view(np.int64)).pin_memory()
+        cols = [t.numpy().view(np.uint64)[c] for c in range(C_)]
+    else:
+        cols = [vals[c].copy() for c in range(C_)]
+    for is_values in (True, False):
+        if is_values:
+            b = engine.PolynomialBatch.from_values(cols, 3, False, 4)
+            assert (b.polynomials == o.coeffs).all()
+        else:
+            b = engine.PolynomialBatch.from_coeffs([o.coeffs[c].copy() for c in range(C_)], 3, False, 4)
+        assert (b.merkle_tree.leaves() == o.leaves).all()
+        assert (b.merkle_tree.digests == o.digests).all() and (b.merkle_tree.cap == o.cap).all()
+    for c in range(C_):
+        assert (cols[c] == vals[c]).all()          # caller's columns untouched
+
+
 def test_get_lde_values(engine, oracle):
     rng = np.random.default_rng(9)
     vals = rand_field(rng, (6, 1 << 6))
