@@ -270,7 +270,10 @@ template <int MODE>
 #ifndef NTT_MINB
 #define NTT_MINB 2
 #endif
-__global__ void __launch_bounds__(512, NTT_MINB) ntt_pass_kernel(NttPass p) {
+#ifndef NTT_LB_THREADS
+#define NTT_LB_THREADS 512
+#endif
+__global__ void __launch_bounds__(NTT_LB_THREADS, NTT_MINB) ntt_pass_kernel(NttPass p) {
     extern __shared__ u64 ntt_smem[];
     u64 *sm = ntt_smem;
     u64 *tw_s = ntt_smem + (size_t)ntt_pitch(p.log_p) * (1u << p.log_a);   // w_P^e table staged once per CTA

@@ -76,14 +76,20 @@ struct NttTableStore {
     }
 };
 
+#ifndef NTT_TILE_LOG
+#define NTT_TILE_LOG 13      // log2 of the elements staged per tile (when the transform is shorter than that)
+#endif
+#ifndef NTT_MAX_THREADS
+#define NTT_MAX_THREADS 512
+#endif
 static inline uint32_t ntt_threads(u32 log_p, u32 log_a) {
     u32 blocks = (1u << (log_p + log_a)) >> 4;  // radix-16 register blocks per tile
     u32 t = blocks < 32 ? 32 : blocks;
-    return t > 512 ? 512 : t;
+    return t > NTT_MAX_THREADS ? NTT_MAX_THREADS : t;
 }
 // lanes per tile: ~8K elements per tile (16K once P >= 2^11), never fewer than 4 lanes (32-byte segments) below 2^13
 static inline u32 ntt_log_a_strided(u32 log_p, u32 log_st) {
-    u32 la = log_p >= 13 ? 0 : 13 - log_p;
+    u32 la = log_p >= NTT_TILE_LOG ? 0 : NTT_TILE_LOG - log_p;
     const u32 la_min = log_p >= 13 ? 1 : 2;   // 2^13-point tiles only fit two lanes in shared memory
     if (la < la_min) la = la_min;
     if (la > 6) la = 6;
@@ -91,7 +97,7 @@ static inline u32 ntt_log_a_strided(u32 log_p, u32 log_st) {
     return la;
 }
 static inline u32 ntt_log_a_contig(u32 log_p) {
-    u32 la = log_p >= 13 ? 0 : 13 - log_p;
+    u32 la = log_p >= NTT_TILE_LOG ? 0 : NTT_TILE_LOG - log_p;
     if (la > 8) la = 8;
     return la;
 }

@@ -39,6 +39,13 @@ struct PsdF64Tables {
     double m_row0[12];           // M[0][j]
     double m_col0[12];           // M[r][0]
     double circ[12];             // MDS_MATRIX_CIRC
+    // split-convolution form (PF_SPLIT): a 12-point circular correlation as (6 cyclic + 6 negacyclic), the cyclic half
+    // again as (3 + 3): 90 FP64 operations instead of 144.  [0..3) = cPP, [3..6) = cPQ, [6..12) = cQ
+    double sc1[12];              // for circ(CIRC)
+    double sc2[12];              // for circ(CIRC)^2
+    double col8[12];             // 8 * CIRC[(12 - r) % 12]:  8 * C e_0
+    double full_init_s[8][2][12];  // chain-init constants in split form [layer][half][UU(3), UV(3), V(6)]
+    double pair_k_s[11][2][12];    // same for the pair constants (lane 0 also carries -8 * pair_t0)
 };
 
 #ifdef __CUDACC__
@@ -77,6 +84,25 @@ static inline void psd_f64_build_tables(PsdF64Tables &t) {
     auto add = [](u64 a, u64 b) { u64 s = a + b; return (s < a || s >= GL_P) ? s - GL_P : s; };
     auto put = [](double (&d)[2], u64 v) { d[0] = (double)(u32)v; d[1] = (double)(u32)(v >> 32); };
     auto rc = [](int round, int lane) -> u64 { return round < 30 ? POSEIDON_RC[12 * round + lane] % GL_P : 0; };
+    // split-convolution constants of a circulant first row c:  cP = (c[i] + c[i+6]) / 2, cQ = (c[i] - c[i+6]) / 2,
+    // cPP = (cP[i] + cP[i+3]) / 2, cPQ = (cP[i] - cP[i+3]) / 2   (halves and quarters are exact in binary64)
+    auto split_row = [](const double (&c)[12], double (&out)[12]) {
+        double cP[6];
+        for (int i = 0; i < 6; i++) { cP[i] = (c[i] + c[i + 6]) / 2; out[6 + i] = (c[i] - c[i + 6]) / 2; }
+        for (int i = 0; i < 3; i++) { out[i] = (cP[i] + cP[i + 3]) / 2; out[3 + i] = (cP[i] - cP[i + 3]) / 2; }
+    };
+    {
+        double c1[12], c2[12];
+        for (int m = 0; m < 12; m++) {
+            c1[m] = (double)circ[m];
+            u64 a = 0;
+            for (int i = 0; i < 12; i++) a += circ[i] * circ[(m - i + 12) % 12];
+            c2[m] = (double)a;
+            t.col8[m] = 8.0 * (double)circ[(12 - m) % 12];
+        }
+        split_row(c1, t.sc1);
+        split_row(c2, t.sc2);
+    }
     const u64 B = PF_BIAS;
     for (int L = 0; L < 8; L++) {
         int next_round = L < 4 ? L + 1 : 27 + (L - 4);   // constants of the round that follows the layer
@@ -93,6 +119,20 @@ static inline void psd_f64_build_tables(PsdF64Tables &t) {
             put(t.pair_k[p][r], k);
         }
     }
+    // the same chain-init constants in split form (same transform as the coefficients)
+    for (int L = 0; L < 8; L++)
+        for (int h = 0; h < 2; h++) {
+            double k[12];
+            for (int j = 0; j < 12; j++) k[j] = t.full_init[L][j][h];
+            split_row(k, t.full_init_s[L][h]);
+        }
+    for (int p = 0; p < 11; p++)
+        for (int h = 0; h < 2; h++) {
+            double k[12];
+            for (int j = 0; j < 12; j++) k[j] = t.pair_k[p][j][h];
+            k[0] -= 8.0 * t.pair_t0[p][h];   // lane 0 receives 8 * T0, T0 = (C W)[0] + 8 W_0 + pair_t0
+            split_row(k, t.pair_k_s[p][h]);
+        }
 }
 
 #ifdef __CUDACC__
@@ -230,8 +270,38 @@ GL_HD void pf_mds(const double (&xl)[12], const double (&xh)[12], int layer, dou
 #endif
 }
 
+// y = init + circ(c) x as a split convolution (see PsdF64Tables::sc1).  cc = split coefficients, init = split constants.
+#ifndef PF_SPLIT
+#define PF_SPLIT 1
+#endif
+GL_HD void pf_circ12(const double (&x)[12], const double *cc, const double *init, double (&y)[12]) {
+    double P[6], Q[6], PP[3], PQ[3], U[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) { P[j] = x[j] + x[j + 6]; Q[j] = x[j] - x[j + 6]; }
+#pragma unroll
+    for (int j = 0; j < 3; j++) { PP[j] = P[j] + P[j + 3]; PQ[j] = P[j] - P[j + 3]; }
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        double uu = init[r], uv = init[3 + r];
+#pragma unroll
+        for (int i = 0; i < 3; i++) uu = pf_fma(PP[(i + r) % 3], cc[i], uu);
+#pragma unroll
+        for (int i = 0; i < 3; i++) uv = (i + r >= 3) ? pf_fma(-PQ[(i + r) % 3], cc[3 + i], uv) : pf_fma(PQ[(i + r) % 3], cc[3 + i], uv);
+        U[r] = uu + uv;
+        U[r + 3] = uu - uv;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        double v = init[6 + r];
+#pragma unroll
+        for (int i = 0; i < 6; i++) v = (i + r >= 6) ? pf_fma(-Q[(i + r) % 6], cc[6 + i], v) : pf_fma(Q[(i + r) % 6], cc[6 + i], v);
+        y[r] = U[r] + v;
+        y[r + 6] = U[r] - v;
+    }
+}
+
 #ifndef PF_SBOX_LANES
-#define PF_SBOX_LANES 6
+#define PF_SBOX_LANES 12
 #endif
 #ifdef __CUDA_ARCH__
 #define PF_UNROLL1 _Pragma("unroll 1")
@@ -268,7 +338,14 @@ GL_HD void pf_full_round(u64 (&s)[12], int layer) {
     }
 #endif
     double al[12], ah[12];
+#if PF_SPLIT
+    pf_circ12(xl, PF_T(sc1), PF_T(full_init_s)[layer][0], al);
+    pf_circ12(xh, PF_T(sc1), PF_T(full_init_s)[layer][1], ah);
+    al[0] = pf_fma(xl[0], 8.0, al[0]);
+    ah[0] = pf_fma(xh[0], 8.0, ah[0]);
+#else
     pf_mds(xl, xh, layer, al, ah);
+#endif
 #pragma unroll
     for (int r = 0; r < 12; r++) s[r] = pf_fold(al[r], ah[r]);
 }
@@ -290,6 +367,27 @@ GL_HD void pf_partial_rounds(u64 (&s)[12]) {
         for (int j = 1; j < 12; j++) pf_renorm(al[j], ah[j]);
         pf_pow7(a, al[0], ah[0]);                       // W
         double t0l = PF_T(pair_t0)[p][0], t0h = PF_T(pair_t0)[p][1];
+#if PF_SPLIT
+        // T0 = (C W)[0] + 8 W_0 + const;  M^2 W = circ(c2) W + W_0 * (8 C e_0) + e_0 * 8 (T0 - const)
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            t0l = pf_fma(al[j], PF_T(circ)[j], t0l);
+            t0h = pf_fma(ah[j], PF_T(circ)[j], t0h);
+        }
+        t0l = pf_fma(al[0], 8.0, t0l);
+        t0h = pf_fma(ah[0], 8.0, t0h);
+        const u64 b = pf_fold(t0l, t0h);                // lane 0 entering the second S-box (RC included)
+        double nl[12], nh[12];                          // M^2 W + K: independent of b, overlaps the S-box below
+        pf_circ12(al, PF_T(sc2), PF_T(pair_k_s)[p][0], nl);
+        pf_circ12(ah, PF_T(sc2), PF_T(pair_k_s)[p][1], nh);
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+            nl[r] = pf_fma(al[0], PF_T(col8)[r], nl[r]);
+            nh[r] = pf_fma(ah[0], PF_T(col8)[r], nh[r]);
+        }
+        nl[0] = pf_fma(t0l, 8.0, nl[0]);
+        nh[0] = pf_fma(t0h, 8.0, nh[0]);
+#else
 #pragma unroll
         for (int j = 0; j < 12; j++) {
             t0l = pf_fma(al[j], PF_T(m_row0)[j], t0l);
@@ -323,6 +421,7 @@ GL_HD void pf_partial_rounds(u64 (&s)[12]) {
 #pragma unroll
             for (int r = 0; r < 12; r++) nh[r] = pf_fma(ah[j], PF_T(m2)[r][j], nh[r]);
         }
+#endif
 #endif
         double bl, bh;
         pf_pow7(b, bl, bh);
