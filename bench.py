@@ -166,6 +166,11 @@ def proof_section(E, log_n, reps=4):
             "reference_published": "~300 s for the real 2^22-row circuit on 32 vCPU (README.md:71); not comparable 1:1"}
 
 
+def exchange_close(exchange):
+    if exchange is not None:
+        exchange.close()
+
+
 def workload_config(cols, log_n, gpus):
     return {"workload": "PolynomialBatch::from_values commit, %d Goldilocks columns x 2^%d rows, rate_bits=3, cap_height=4 "
                         "(BASELINE.json configs[1])" % (cols, log_n),
@@ -185,6 +190,8 @@ def main():
     ap.add_argument("--cols", type=int, default=135)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--proof-log-n", type=int, default=20, help="rows (log2) of the synthetic circuit-shaped proof; 0 = skip")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: column->row exchange fused into the LDE's last pass as NVLink peer stores (default), or NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -211,6 +218,7 @@ def main():
     log_n = args.log_n + (world.bit_length() - 1)
     n = 1 << log_n
     plan = E.ShardPlan(cols, log_n, RATE_BITS, CAP_HEIGHT, world) if distributed else None
+    exchange = E.PeerExchange(plan, rank, torch.device("cuda", local_rank)) if distributed and args.exchange == "peer" else None
     my_cols = plan.columns_of(rank) if distributed else range(cols)
     # synthetic witness, generated on the host, pinned for the e2e path
     host = torch.from_numpy(E.splitmix_columns(len(my_cols), n, first_col=my_cols.start).view(np.int64)).pin_memory()
@@ -226,7 +234,7 @@ def main():
 
     def step_device():
         if distributed:
-            b = E.ShardedPolynomialBatch.from_values(dev, plan, rank)
+            b = E.ShardedPolynomialBatch.from_values(dev, plan, rank, exchange=exchange)
             return {k: 0.0 for k in stage_keys}
         b = E.PolynomialBatch.from_values(dev, RATE_BITS, False, CAP_HEIGHT)
         ms = b.stage_ms()
@@ -236,7 +244,7 @@ def main():
     def step_e2e():
         if distributed:
             staged = host.cuda(non_blocking=True)          # H2D of this rank's columns
-            b = E.ShardedPolynomialBatch.from_values(staged, plan, rank)
+            b = E.ShardedPolynomialBatch.from_values(staged, plan, rank, exchange=exchange)
             return b.cap                                   # replicated cap, already on the host
         b = E.PolynomialBatch.from_values(host_cols, RATE_BITS, False, CAP_HEIGHT)
         cap = b.merkle_tree.cap            # D2H read of the result
@@ -298,9 +306,12 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "GB/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": 8 * cols * n, "d2h_bytes_per_step": (32 << CAP_HEIGHT) * world},
                 "gpu_launches": launches, "clocks": clocks, "cap0": "%016x" % int(cap_e2e[0][0]),
-                "exchange": "all_to_all_single of %.2f GB per rank (NCCL), cap all_gather" % (8 * len(my_cols) * (n << RATE_BITS) * (world - 1) / world / 1e9),
+                "exchange": ("fused: the LDE's last pass stores %.2f GB per rank into the peers' leaf matrices (NVLink P2P, CUDA IPC); NCCL carries two "
+                             "barriers and the cap all_gather" if exchange is not None else
+                             "all_to_all_single of %.2f GB per rank (NCCL), cap all_gather") % (8 * len(my_cols) * (n << RATE_BITS) * (world - 1) / world / 1e9),
             }
-            print(json.dumps(line))
+            print(json.dumps(line), flush=True)
+            exchange_close(exchange)
             dist.destroy_process_group()
             return
         leaf_ms = stages["build Merkle tree (leaves)"]
@@ -340,8 +351,9 @@ def main():
                                     "sample": "one commit of %d columns x 2^%d rows (rate_bits 3, cap_height 4), %.1f s; C++/OpenMP "
                                               "restatement of plonky2's CPU algorithm, not the Rust prover" % (cols, k, dt),
                                     "stage_s": cpu_stages}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if distributed:
+        exchange_close(exchange)      # collective: every rank
         dist.destroy_process_group()
 
 

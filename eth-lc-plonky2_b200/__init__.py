@@ -8,7 +8,7 @@ from . import build as _build_mod
 from ._lib import (ENG_ERR_CUDA, ENG_ERR_INVALID, ENG_ERR_OOM, ENG_ERR_STATE, ENG_OK, EngineError, exported_symbols, init,
                    launch_count, load, measure_int_peak, set_stream, so_path, synchronize)
 from .synthetic import splitmix_columns
-from .parallel import EngineOps, ShardedPolynomialBatch, ShardPlan
+from .parallel import EngineOps, PeerExchange, ShardedPolynomialBatch, ShardPlan
 from .plonky2 import Circuit, synth_circuit
 from .plonky2 import Challenger, FriInstanceInfo, FriParams, FriProof, reduction_arity_bits
 from .plonky2 import SALT_SIZE, MerkleTree, PolynomialBatch, PoseidonHash, poseidon

@@ -637,6 +637,74 @@ eng_status eng_lde_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_t log
     return ENG_OK;
 }
 
+// ---- fused exchange: the LDE's last pass stores straight into the row-shard owners' leaf matrices (NVLink P2P) ----
+eng_status eng_lde_peer_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits, int32_t is_values,
+                            uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *scratch_dev, uint64_t *const *shard_out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!src_dev || !coeffs_out_dev || !scratch_dev || !shard_out) return fail(ENG_ERR_INVALID, "NULL buffer");
+    if (num_polys == 0) return fail(ENG_ERR_INVALID, "no polynomials");
+    if (log_n > 2 * NTT_MAX_LOGP || log_n + rate_bits > 32) return fail(ENG_ERR_INVALID, "size unsupported");
+    if (((u64)1 << log_row_shards) > NTT_MAX_SHARDS) return fail(ENG_ERR_INVALID, "more than %d row shards", NTT_MAX_SHARDS);
+    for (u32 gi = 0; gi < (1u << log_row_shards); gi++)
+        if (!shard_out[gi]) return fail(ENG_ERR_INVALID, "shard_out[%u] is NULL", gi);
+    const u64 n = (u64)1 << log_n;
+    std::vector<NttLaunch> plan;
+    if (is_values) {
+        if (!ntt_plan_intt(g.tables, src_dev, n, scratch_dev, n, coeffs_out_dev, n, num_polys, log_n, plan))
+            return fail(ENG_ERR_INVALID, "iNTT size unsupported");
+        ST(launch_plan(plan));
+    } else if (src_dev != coeffs_out_dev) {
+        CU(cudaMemcpyAsync(coeffs_out_dev, src_dev, (size_t)num_polys * n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+    }
+    plan.clear();
+    if (!ntt_plan_lde(g.tables, coeffs_out_dev, n, scratch_dev, num_polys, log_n, rate_bits, log_row_shards, plan, shard_out))
+        return fail(ENG_ERR_INVALID, "LDE shape unsupported (log_n=%u rate_bits=%u log_row_shards=%u)", log_n, rate_bits, log_row_shards);
+    ST(launch_plan(plan));
+    return ENG_OK;
+}
+
+// Exchange buffers live outside the stream-ordered pool (cudaMalloc) so that they can be exported over CUDA IPC.
+eng_status eng_peer_buffer_alloc(uint64_t num_elems, uint64_t **dev_out, uint8_t handle_out[64]) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!dev_out || !handle_out || num_elems == 0) return fail(ENG_ERR_INVALID, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, num_elems * sizeof(u64));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ENG_ERR_OOM, "cudaMalloc of %llu bytes failed: %s", (unsigned long long)(num_elems * 8), cudaGetErrorString(e)); }
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); cudaGetLastError(); return fail(ENG_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle_out, &h, 64);
+    *dev_out = (uint64_t *)p;
+    return ENG_OK;
+}
+eng_status eng_peer_buffer_open(const uint8_t handle[64], uint64_t **dev_out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!handle || !dev_out) return fail(ENG_ERR_INVALID, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_out = (uint64_t *)p;
+    return ENG_OK;
+}
+eng_status eng_peer_buffer_close(uint64_t *peer_ptr) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!peer_ptr) return ENG_OK;
+    CU(cudaIpcCloseMemHandle(peer_ptr));
+    return ENG_OK;
+}
+eng_status eng_peer_buffer_free(uint64_t *dev_ptr) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!dev_ptr) return ENG_OK;
+    CU(cudaDeviceSynchronize());
+    CU(cudaFree(dev_ptr));
+    return ENG_OK;
+}
+
 eng_status eng_batch_free(eng_batch *b) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!b) return ENG_OK;

@@ -19,6 +19,7 @@
 #include "gl64.cuh"
 
 #define NTT_MAX_LOGP 13
+#define NTT_MAX_SHARDS 16
 
 enum NttMode : int {
     NTT_LDE_FIRST = 0,   // coeffs (strided tile) * shift powers -> DIF -> * w_n^{r k1} -> block b, in-place order
@@ -46,6 +47,11 @@ struct NttPass {
     // shards the buffer is [G][C][L/G], i.e. the all-to-all send chunks of the multi-GPU commit are contiguous.
     u32 log_shard_rows;
     u64 shard_stride;
+    // Fused exchange (multi-GPU): when num_shard_ptrs != 0 the LAST pass of the LDE stores row shard g through
+    // shard_out[g] instead of out + g * shard_stride -- shard_out[g] is a peer-mapped pointer (NVLink P2P) to where this
+    // rank's [C_r][L/G] block lives inside row-shard owner g's [C][L/G] leaf matrix, so the all-to-all is the store.
+    u32 num_shard_ptrs;
+    u64 *shard_out[NTT_MAX_SHARDS];
     const u64 *tw_local;  // w_P^e (or inverse), e < P/2
     const u64 *w_lo, *w_hi;  // w_n^e = w_hi[e >> w_lo_bits] * w_lo[e & mask]   (or inverse powers)
     u32 w_lo_bits;
@@ -205,15 +211,20 @@ GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nth
             u32 e = (u32)(unit & ((1u << p.rate_bits) - 1));
             u32 b = ntt_brev(e, p.rate_bits);
             u64 k = ((u64)b << p.log_n) + q;
-            if (col < p.num_cols)
-                p.out[(k >> p.log_shard_rows) * p.shard_stride + col * p.out_col_stride + (k & (((u64)1 << p.log_shard_rows) - 1))] =
-                    gl_canon(sm[ntt_sm(pitch, a, q)]);
+            if (col < p.num_cols) {
+                u64 *base = p.num_shard_ptrs ? p.shard_out[k >> p.log_shard_rows] : p.out + (k >> p.log_shard_rows) * p.shard_stride;
+                base[col * p.out_col_stride + (k & (((u64)1 << p.log_shard_rows) - 1))] = gl_canon(sm[ntt_sm(pitch, a, q)]);
+            }
         }
     } else if (MODE == NTT_DIF_LAST) {
         for (u32 idx = tid; idx < total; idx += nthreads) {
             u32 q = idx & (P - 1), a = idx >> p.log_p;
             u64 unit = tile * A + a;
-            if (unit < p.num_units) p.out[(unit << p.log_p) + q] = gl_canon(sm[ntt_sm(pitch, a, q)]);
+            if (unit < p.num_units) {
+                u64 i0 = unit << p.log_p;   // a run never straddles row shards (shard_stride is a multiple of P)
+                u64 *dst = p.num_shard_ptrs ? p.shard_out[i0 / p.shard_stride] + i0 % p.shard_stride : p.out + i0;
+                dst[q] = gl_canon(sm[ntt_sm(pitch, a, q)]);
+            }
         }
     } else if (MODE == NTT_INTT_P1) {
         // Y[col][(r0+a) * P + k2], k2 = brev(q), times w_n^{-(r0+a) k2}

@@ -146,8 +146,10 @@ static inline bool ntt_plan_intt(NttTableStore &ts, const u64 *in, u64 in_stride
 
 // coeffs [C][n] -> lde (column-major, bit-reversed rows), shift 7, as 2^log_shards row shards: [G][C][L/G]
 // (log_shards = 0: the plain [C][L] layout).  Returns false if the shape is unsupported.
+// shard_out (optional, 2^log_shards pointers): the last pass stores row shard g at shard_out[g] ([C][L/G], possibly
+// peer memory) instead of lde + g * C * L/G; lde is then only the local intermediate of the first pass.
 static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs_stride, u64 *lde, u32 C, u32 log_n,
-                                u32 rate_bits, u32 log_shards, std::vector<NttLaunch> &plan) {
+                                u32 rate_bits, u32 log_shards, std::vector<NttLaunch> &plan, u64 *const *shard_out = nullptr) {
     if (log_n > 2 * NTT_MAX_LOGP) return false;
     const u32 log_l = log_n + rate_bits;
     if (log_shards > log_l) return false;
@@ -157,6 +159,13 @@ static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs
     p.out_col_stride = (u64)1 << p.log_shard_rows;
     p.shard_stride = (u64)C << p.log_shard_rows;
     p.in = coeffs; p.in_col_stride = coeffs_stride; p.out = lde;
+    if (shard_out && log_shards > 4) return false;
+    auto set_shard_ptrs = [&](NttPass &q) {
+        q.num_shard_ptrs = 0;
+        if (!shard_out) return;
+        q.num_shard_ptrs = 1u << log_shards;
+        for (u32 g = 0; g < q.num_shard_ptrs; g++) q.shard_out[g] = shard_out[g];
+    };
     if (log_n <= NTT_MAX_LOGP) {
         auto s = ts.shift(log_n, rate_bits, log_n);  // st = 1: a[e][j] = s_e^j is the whole table
         p.shift_a = s.a; p.shift_b = s.a;
@@ -164,6 +173,7 @@ static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs
         u64 units = (u64)C << rate_bits;
         p.num_tiles = (units + (1u << p.log_a) - 1) >> p.log_a;
         p.tw_local = ts.tw_local(log_n, false);
+        set_shard_ptrs(p);
         plan.push_back(ntt_make_launch(NTT_LDE_SINGLE, p));
         return true;
     }
@@ -183,6 +193,7 @@ static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs
     p.num_units = units;
     p.num_tiles = (units + (1u << p.log_a) - 1) >> p.log_a;
     p.tw_local = ts.tw_local(lst, false);
+    set_shard_ptrs(p);
     plan.push_back(ntt_make_launch(NTT_DIF_LAST, p));
     return true;
 }

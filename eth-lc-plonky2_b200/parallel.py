@@ -12,6 +12,12 @@ PolynomialBatch::from_values across the GPUs of one box, one process per GPU:
      `digests` of the global tree are the concatenation of the per-rank digests in rank order;
   4. a (2^cap_height x 32 B) all-gather replicates the cap.
 
+Fused exchange (PeerExchange, the default on GPUs): steps 1 and 2 are ONE kernel.  Every rank exports its [C][L/G] leaf
+matrix over CUDA IPC; the last pass of the LDE stores row shard g straight into rank g's matrix through the peer
+mapping (NVLink P2P stores issued tile by tile as the transform finishes them), so no send buffer is written, re-read
+or copied and NCCL only carries the two barriers and the cap all-gather.  The NCCL all-to-all path stays for gloo (CPU
+tests) and as the A/B baseline.
+
 Coefficients stay column-sharded, leaves and digests row-sharded.  The local operators are injected (`ops`) so that
 the host-side index logic can be exercised on CPU with gloo; the default operators call the CUDA engine.
 """
@@ -91,6 +97,62 @@ class EngineOps:
         return t.cpu().numpy().view(np.uint64)
 
 
+class _DevArray:
+    """Exposes raw device memory to torch (torch.as_tensor) through __cuda_array_interface__."""
+
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+class PeerExchange:
+    """Receive side of the fused exchange for one ShardPlan: this rank's [C][L/G] leaf matrix (allocated outside the pool,
+    exported over CUDA IPC) and the peer mappings of everybody else's.  Collective constructor; reusable across steps."""
+
+    def __init__(self, plan, rank, device, group=None, dist=None):
+        import torch
+        if dist is None:
+            import torch.distributed as dist
+        self.plan, self.rank, self.group, self.dist = plan, rank, group, dist
+        lib = _lib.lib()
+        elems = plan.num_polys * plan.rows_per_rank
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        check(lib.eng_peer_buffer_alloc(elems, C.byref(ptr), handle))
+        self.local_ptr = ptr.value
+        handles = [None] * plan.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.bases, self._opened = [], []
+        for g in range(plan.world):
+            if g == rank:
+                self.bases.append(self.local_ptr)
+            else:
+                q = C.c_void_p()
+                check(lib.eng_peer_buffer_open(handles[g], C.byref(q)))
+                self.bases.append(q.value)
+                self._opened.append(q.value)
+        off = plan.col_offsets[rank] * plan.rows_per_rank * 8     # this rank's first column inside every leaf matrix
+        self.shard_out = (C.c_void_p * plan.world)(*[b + off for b in self.bases])
+        self.recv = torch.as_tensor(_DevArray(self.local_ptr, elems), device=device)
+        self._token = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def barrier(self):
+        self.dist.all_reduce(self._token, group=self.group)
+        self._token.zero_()
+        import torch
+        torch.cuda.synchronize()
+
+    def close(self):
+        lib = _lib.lib()
+        self.barrier()
+        for q in self._opened:
+            lib.eng_peer_buffer_close(C.c_void_p(q))
+        self._opened = []
+        self.barrier()
+        if self.local_ptr:
+            lib.eng_peer_buffer_free(C.c_void_p(self.local_ptr))
+            self.local_ptr = None
+
+
 class ShardedPolynomialBatch:
     """PolynomialBatch whose polynomials are column-sharded and whose leaves / digests are row-sharded."""
 
@@ -98,9 +160,10 @@ class ShardedPolynomialBatch:
         self.plan, self.rank, self.coeffs, self.rows, self.merkle_tree_local, self.cap, self.ops = plan, rank, coeffs, rows, tree, cap, ops
 
     @classmethod
-    def from_values(cls, local_values, plan, rank, group=None, ops=None, is_values=True, dist=None):
+    def from_values(cls, local_values, plan, rank, group=None, ops=None, is_values=True, dist=None, exchange=None):
         """local_values: [plan.col_counts[rank]][2^log_n] tensor holding this rank's columns (values, or coefficients
-        when is_values is False).  Collective over `group` (torch.distributed)."""
+        when is_values is False).  Collective over `group` (torch.distributed).  With `exchange` (a PeerExchange of the
+        same plan) the column->row exchange is fused into the LDE's last pass; its leaf matrix is reused by every call."""
         if dist is None:
             import torch.distributed as dist
         if ops is None:
@@ -110,6 +173,32 @@ class ShardedPolynomialBatch:
         if tuple(local_values.shape) != (c_r, n):
             raise EngineError(_lib.ENG_ERR_INVALID, "rank %d expects a [%d][%d] column shard, got %s" % (rank, c_r, n, tuple(local_values.shape)))
         coeffs = ops.empty(c_r * n).view(c_r, n)
+        if exchange is not None and plan.world > 1:
+            import os, time
+            trace = os.environ.get("ENG_TRACE")
+            t0 = time.perf_counter()
+            scratch = ops.empty(c_r * (n << plan.rate_bits))
+            exchange.barrier()                       # every rank has finished reading its leaf matrix of the previous call
+            t1 = time.perf_counter()
+            check(_lib.lib().eng_lde_peer_dev(C.c_void_p(local_values.data_ptr()), c_r, plan.log_n, plan.rate_bits, int(is_values),
+                                              plan.log_world, C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                              exchange.shard_out))
+            _lib.synchronize()
+            t2 = time.perf_counter()
+            exchange.barrier()                       # every rank's stores have landed
+            t3 = time.perf_counter()
+            del scratch
+            recv = exchange.recv
+            tree = ops.merkle(recv, plan.num_polys, plan.rows_per_rank, plan.local_cap_height)
+            local_cap = ops.to_tensor(tree.cap).reshape(-1)
+            t4 = time.perf_counter()
+            parts = [ops.empty(local_cap.numel()) for _ in range(plan.world)]
+            dist.all_gather(parts, local_cap, group=group)
+            cap = np.concatenate([ops.to_numpy(p).reshape(-1, 4) for p in parts])
+            if trace:
+                print("rank %d: alloc+barrier %.1f  lde %.1f  barrier %.1f  merkle+cap %.1f  gather %.1f ms" % (
+                    rank, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3), 1e3 * (time.perf_counter() - t4)), flush=True)
+            return cls(plan, rank, coeffs, recv.view(plan.num_polys, plan.rows_per_rank), tree, cap, ops)
         send = ops.empty(c_r * (n << plan.rate_bits))
         ops.lde(local_values, is_values, plan.log_n, plan.rate_bits, plan.log_world, coeffs, send)   # [G][C_r][L/G]
         recv = ops.empty(plan.num_polys * plan.rows_per_rank)                                          # [C][L/G]

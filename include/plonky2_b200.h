@@ -85,6 +85,20 @@ eng_status eng_batch_free(eng_batch *b);
 eng_status eng_lde_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits, int32_t is_values,
                        uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *lde_out_dev);
 
+/* Fused exchange: the same transforms, but the LAST pass of the LDE stores row shard g through
+ * shard_out[g] -- a device pointer, normally a peer mapping (NVLink P2P) into row-shard owner g's leaf matrix
+ * [C][L/G] at this rank's first column -- so the column->row all-to-all is the store itself and no send buffer is
+ * re-read.  scratch_dev ([num_polys][L], local) holds the first pass' intermediate.  The caller synchronises all ranks
+ * (stream sync + barrier) before hashing the received rows.  log_row_shards <= 4. */
+eng_status eng_lde_peer_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits, int32_t is_values,
+                            uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *scratch_dev, uint64_t *const *shard_out);
+/* Exchange buffers: device memory outside the stream-ordered pool, exportable to the other ranks of the box through a
+ * 64-byte CUDA IPC handle (cudaIpcGetMemHandle / cudaIpcOpenMemHandle). */
+eng_status eng_peer_buffer_alloc(uint64_t num_elems, uint64_t **dev_out, uint8_t handle_out[64]);
+eng_status eng_peer_buffer_open(const uint8_t handle[64], uint64_t **dev_out);
+eng_status eng_peer_buffer_close(uint64_t *peer_ptr);
+eng_status eng_peer_buffer_free(uint64_t *dev_ptr);
+
 /* ---- a3: MerkleTree::new(leaves, cap_height)  [plonky2:hash/merkle_tree.rs] ----
  * leaves_host is row-major [num_leaves][leaf_len].  ENG_ERR_INVALID when cap_height > log2(num_leaves) or
  * num_leaves is not a power of two (plonky2 panics). */

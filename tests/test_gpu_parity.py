@@ -271,3 +271,37 @@ def test_row_sharded_path_emulated_on_one_gpu(engine, oracle, world):
     if world == 1:
         b = E.ShardedPolynomialBatch.from_values(ops.to_tensor(vals), plan, 0)
         assert (b.cap == ref.cap).all() and (b.prove(77) == ref.prove(77)).all()
+
+
+@pytest.mark.parametrize("world,log_n", [(2, 13), (4, 13), (8, 15), (2, 9), (16, 14)])
+def test_fused_exchange_stores_emulated_on_one_gpu(engine, oracle, world, log_n):
+    """eng_lde_peer_dev: the LDE's last pass stores row shard g through shard_out[g].  Here the 'peer' leaf matrices are
+    ordinary local buffers (one per emulated rank), so the store addressing of the fused exchange is checked without
+    CUDA IPC; the real peer mappings are exercised by bench.py --gpus N (its cap must equal the NCCL path's)."""
+    import ctypes as C
+    import torch
+    from eth_lc_plonky2_b200._lib import check, lib, synchronize
+    E = engine
+    C_, r, h = 19, 3, 4
+    vals = rand_field(np.random.default_rng(100 + world), (C_, 1 << log_n), noncanonical=True)
+    ref = oracle.Batch.from_values(vals, r, h)
+    plan = E.ShardPlan(C_, log_n, r, h, world)
+    ops = E.EngineOps(torch.device("cuda", 0))
+    mats = [ops.empty(C_ * plan.rows_per_rank) for _ in range(world)]          # rank g's [C][L/G]
+    for rank in range(world):
+        cols = plan.columns_of(rank)
+        local = ops.to_tensor(vals[cols.start:cols.stop])
+        coeffs = ops.empty(len(cols) << log_n).view(len(cols), 1 << log_n)
+        scratch = ops.empty(len(cols) << (log_n + r))
+        shard_out = (C.c_void_p * world)(*[m.data_ptr() + plan.col_offsets[rank] * plan.rows_per_rank * 8 for m in mats])
+        check(lib().eng_lde_peer_dev(C.c_void_p(local.data_ptr()), len(cols), log_n, r, 1, plan.log_world,
+                                     C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), shard_out))
+        synchronize()
+        assert (ops.to_numpy(coeffs) == ref.coeffs[cols.start:cols.stop]).all()
+    caps = []
+    for g in range(world):
+        lo = g * plan.rows_per_rank
+        got = ops.to_numpy(mats[g]).reshape(C_, plan.rows_per_rank)
+        assert (got.T == ref.leaves[lo:lo + plan.rows_per_rank]).all()
+        caps.append(ops.merkle(mats[g], C_, plan.rows_per_rank, plan.local_cap_height).cap)
+    assert (np.concatenate(caps) == ref.cap).all()
