@@ -31,6 +31,10 @@ sys.path.insert(0, ROOT)
 RATE_BITS = 3
 CAP_HEIGHT = 4
 IMAD_PER_PERM = 6612
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures at configs[1]
+# (profiles/r01_leaves_v1.md, profiles/r01_ntt_v2.md); only quoted when the workload is that configuration
+NCU_TRAFFIC_LEAVES = 9.086e9 + 0.330e9
+NCU_TRAFFIC_NTT = (1.74 + 9.23 + 9.06 + 9.24) * 1e9 + 4 * 1.13e9
 NOMINAL_IMAD_PER_S = 148 * 64 * 1.965e9   # 64 IMAD/clk/SM; no integer entry in MEASURED_PEAKS.json
 
 
@@ -331,14 +335,18 @@ def main():
             "stage_ms": stages,
             "roofline": {"kernel": "merkle_leaves_kernel (Poseidon leaf hashing, %d permutations per launch)" % leaf_perms,
                          "bound": "int32-imad", "achieved": imad_rate / 1e12, "peak": NOMINAL_IMAD_PER_S / 1e12,
-                         "unit": "TIMAD32/s", "frac": imad_rate / NOMINAL_IMAD_PER_S, "traffic": None,
+                         "unit": "TIMAD32/s", "frac": imad_rate / NOMINAL_IMAD_PER_S,
+                         "traffic": NCU_TRAFFIC_LEAVES if (cols, log_n) == (135, 20) else None,
+                         "hbm_floor_ms": (8 * cols * L + 32 * L) / (peaks["hbm_gbs"] * 1e9) * 1e3,
                          "peak_kind": "nominal 148 SM x 64 IMAD/clk x 1.965 GHz (no measured integer peak in MEASURED_PEAKS.json)",
                          "perms_per_s": leaf_perms / (leaf_ms * 1e-3), "kernel_ms": leaf_ms,
                          "measured_issue_rates_Tops": {k: v / 1e12 for k, v in int_peak.items()},
                          "frac_of_measured_imad": imad_rate / int_peak["imad"]},
             "roofline_hbm": {"kernel": "ntt_pass_kernel x4 (iNTT 2 passes + coset LDE 2 passes)", "bound": "hbm",
                              "achieved": hbm_rate, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_rate / peaks["hbm_gbs"],
-                             "traffic": None, "peak_kind": peak_kind, "kernel_ms": ntt_ms, "algorithmic_bytes": b_ntt(cols, n)},
+                             "traffic": NCU_TRAFFIC_NTT if (cols, log_n) == (135, 20) else None, "peak_kind": peak_kind,
+                             "note": "integer-issue bound, not HBM bound: ~40 alu instructions per butterfly on the half-rate alu pipe "
+                                     "(profiles/r01_ntt_v2.md); reported against the HBM roof because BASELINE.json asks for it", "kernel_ms": ntt_ms, "algorithmic_bytes": b_ntt(cols, n)},
             "clocks": clocks,
             "cap0": "%016x" % int(cap_e2e[0][0]),
         }
