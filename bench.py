@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--cols", type=int, default=135)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--proof-log-n", type=int, default=20, help="rows (log2) of the synthetic circuit-shaped proof; 0 = skip")
+    ap.add_argument("--proof-full-log-n", type=int, default=22, help="rows (log2) of the full-size synthetic proof; 0 = skip")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: column->row exchange fused into the LDE's last pass as NVLink peer stores (default), or NCCL all-to-all")
     args = ap.parse_args()
@@ -352,6 +353,9 @@ def main():
         }
         if args.proof_log_n:
             line["proof"] = proof_section(E, args.proof_log_n)
+        if args.proof_full_log_n:
+            # the eth-lc circuit's own size (~2.98 M constraints => 2^22 rows, BASELINE configs[3]); same synthetic gate set
+            line["proof_full_size"] = proof_section(E, args.proof_full_log_n, reps=3)
         if not args.no_cpu_baseline and world == 1:
             k = cpu_sample_log_n(cols)
             dt, cpu_stages, threads = cpu_commit(cols, k)

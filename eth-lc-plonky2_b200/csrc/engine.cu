@@ -143,7 +143,7 @@ template <int MODE>
 eng_status launch_mode(const NttLaunch &l) {
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(ntt_pass_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(ntt_pass_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CU(cudaFuncSetAttribute(ntt_pass_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }

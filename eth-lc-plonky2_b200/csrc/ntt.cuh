@@ -52,7 +52,7 @@ struct NttPass {
     // rank's [C_r][L/G] block lives inside row-shard owner g's [C][L/G] leaf matrix, so the all-to-all is the store.
     u32 num_shard_ptrs;
     u64 *shard_out[NTT_MAX_SHARDS];
-    const u64 *tw_local;  // w_P^e (or inverse), e < P/2
+    const u64 *tw_local;  // w_P^e (or inverse), e < P
     const u64 *w_lo, *w_hi;  // w_n^e = w_hi[e >> w_lo_bits] * w_lo[e & mask]   (or inverse powers)
     u32 w_lo_bits;
     const u64 *shift_a, *shift_b;  // LDE: s_e^{j*st} [e][P]  and  s_e^{r} [e][st];  s_e = 7 * w_L^e
@@ -71,8 +71,8 @@ GL_HD u32 ntt_brev(u32 x, u32 bits) {
 
 GL_HD u32 ntt_pitch(u32 log_p) { u32 P = 1u << log_p; return P + (P >> 4) + 1; }
 GL_HD u32 ntt_sm(u32 pitch, u32 a, u32 j) { return a * pitch + j + (j >> 4); }
-static inline size_t ntt_smem_bytes(u32 log_p, u32 log_a) {  // tile + the w_P^e table
-    return ((size_t)ntt_pitch(log_p) * (1u << log_a) + ((1u << log_p) >> 1) + 1) * sizeof(u64);
+static inline size_t ntt_smem_bytes(u32 log_p, u32 log_a) {  // tile + the w_P^e table (all P powers)
+    return ((size_t)ntt_pitch(log_p) * (1u << log_a) + (1u << log_p) + 1) * sizeof(u64);
 }
 
 GL_HD u64 ntt_twiddle2(const NttPass &p, u64 e) {
@@ -140,29 +140,246 @@ GL_HD void ntt_round(const NttPass &p, u64 *sm, const u64 *tw, u32 t0, u32 tid, 
     const u32 blocks_per_lane = P >> R;
     const u32 nblocks = blocks_per_lane << p.log_a;
     const u32 log_js = p.log_p - t0 - R;  // log2 of the element stride inside the register block
+    // Addressing is kept off the alu pipe: the 16 slots of a register block are base + m * step (the padding j >> 4 is
+    // linear in m whenever the element stride is 1 or a multiple of 16), and a twiddle exponent is
+    // (lo << s_u) + m' * 2^(log_js + s_u) -- one IMAD each instead of shift/add/shift/add chains.
+    const u32 log_bpl = p.log_p - R;
+    const bool linear = (log_js >= 4) || (log_js == 0);
+    const u32 step = log_js >= 4 ? ((1u << log_js) + (1u << (log_js - 4))) : 1u;
     for (u32 blk = tid; blk < nblocks; blk += nthreads) {
-        u32 a = blk / blocks_per_lane, T = blk % blocks_per_lane;
+        u32 a = blk >> log_bpl, T = blk & (blocks_per_lane - 1);
         u32 lo = T & ((1u << log_js) - 1), hi = T >> log_js;
         u32 jb = (hi << (p.log_p - t0)) + lo;
+        const u32 base = ntt_sm(pitch, a, jb);
         u64 v[1 << R];
+        if (linear) {
 #pragma unroll
-        for (int m = 0; m < (1 << R); m++) v[m] = sm[ntt_sm(pitch, a, jb + ((u32)m << log_js))];
+            for (int m = 0; m < (1 << R); m++) v[m] = sm[base + (u32)m * step];
+        } else {
+#pragma unroll
+            for (int m = 0; m < (1 << R); m++) v[m] = sm[ntt_sm(pitch, a, jb + ((u32)m << log_js))];
+        }
 #pragma unroll
         for (int u = 1; u <= R; u++) {
             const int span = 1 << (R - u);
+            const u32 su = t0 + u - 1;
+            const u32 e0 = lo << su, em = 1u << (log_js + su);   // exponent of register m' = e0 + m' * em
 #pragma unroll
             for (int m = 0; m < (1 << R); m++) {
                 if (m & span) continue;
                 // pair (j, j + half), half = span << log_js; twiddle w_P^{(j mod half) << (t0+u-1)}
-                u32 jm = (((u32)m & (span - 1)) << log_js) + lo;
                 u64 x = v[m], y = v[m + span];
                 v[m] = gl_add(x, y);
                 if (LAST && (m & (span - 1)) == 0) v[m + span] = gl_sub(x, y);  // w = 1
-                else v[m + span] = gl_mul(gl_sub(x, y), tw[jm << (t0 + u - 1)]);
+                else v[m + span] = gl_mul(gl_sub(x, y), tw[e0 + (u32)(m & (span - 1)) * em]);
             }
         }
+        if (linear) {
 #pragma unroll
-        for (int m = 0; m < (1 << R); m++) sm[ntt_sm(pitch, a, jb + ((u32)m << log_js))] = v[m];
+            for (int m = 0; m < (1 << R); m++) sm[base + (u32)m * step] = v[m];
+        } else {
+#pragma unroll
+            for (int m = 0; m < (1 << R); m++) sm[ntt_sm(pitch, a, jb + ((u32)m << log_js))] = v[m];
+        }
+    }
+}
+
+
+// ---- radix-16 round as ONE 16-point DFT with power-of-two twiddles + one twiddle product per output ----------------
+// In Goldilocks 2 has order 192 and plonky2's roots of unity satisfy w_16 = 2^156, w_8 = 2^120, w_4 = 2^48 (w_16 is
+// h_gl_root_of_unity(4); checked by tests/test_replay.py), so every twiddle INSIDE a 16-point DFT is a shift.  The four
+// stages of a radix-16 block multiply the lower branch of stage u by w_{2^(5-u)}^{m'} * tau^(2^(u-1)), tau =
+// w_P^(lo << t0); the tau factors commute to the outputs: register r leaves the pure DFT times tau^bitrev4(r).  So a
+// block is 64 additions / subtractions, 17 shifts and 15 (instead of 32) twiddle products.  The additions run LAZILY on
+// 96-bit two's-complement values (3 instructions each, no wrap correction); a value is reduced once, before its product.
+struct gl96 {
+    u32 w0, w1, w2;   // w0 + 2^32 w1 + 2^64 (int32)w2
+};
+GL_HD gl96 l3_from(u64 x) { gl96 r; r.w0 = (u32)x; r.w1 = (u32)(x >> 32); r.w2 = 0; return r; }
+#ifndef __CUDA_ARCH__
+typedef __int128 l3_i128;
+GL_HD l3_i128 l3_val(gl96 a) { return (l3_i128)a.w0 + ((l3_i128)a.w1 << 32) + ((l3_i128)(int32_t)a.w2) * ((l3_i128)1 << 64); }
+GL_HD gl96 l3_make(l3_i128 v) {
+    gl96 r; r.w0 = (u32)v; r.w1 = (u32)(v >> 32); r.w2 = (u32)(v >> 64);
+    return r;   // callers stay far below 2^95; the GPU code wraps identically
+}
+#endif
+GL_HD gl96 l3_add(gl96 a, gl96 b) {
+#ifdef __CUDA_ARCH__
+    gl96 r;
+    asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
+        : "=&r"(r.w0), "=&r"(r.w1), "=r"(r.w2) : "r"(a.w0), "r"(a.w1), "r"(a.w2), "r"(b.w0), "r"(b.w1), "r"(b.w2));
+    return r;
+#else
+    return l3_make(l3_val(a) + l3_val(b));
+#endif
+}
+GL_HD gl96 l3_sub(gl96 a, gl96 b) {
+#ifdef __CUDA_ARCH__
+    gl96 r;
+    asm("sub.cc.u32 %0, %3, %6;\n\tsubc.cc.u32 %1, %4, %7;\n\tsubc.u32 %2, %5, %8;"
+        : "=&r"(r.w0), "=&r"(r.w1), "=r"(r.w2) : "r"(a.w0), "r"(a.w1), "r"(a.w2), "r"(b.w0), "r"(b.w1), "r"(b.w2));
+    return r;
+#else
+    return l3_make(l3_val(a) - l3_val(b));
+#endif
+}
+// x * 2^S (mod p) for a lazy x with |x| < 2^80, 0 < S < 96, S = 32 a + b.  Y = x << b is the 128-bit two's-complement
+// number (y0, y1, y2, y3); 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32, 2^160 = 1 - 2^32 (mod p) give
+//   a = 0:  (y0 - y2 - y3) + 2^32 (y1 + y2)        a = 1:  (-y1 - y2) + 2^32 (y0 + y1 - y3)
+//   a = 2:  (-y0 - y1 + y3) + 2^32 (y0 - y2 - y3)
+template <int S>
+GL_HD gl96 l3_shl(gl96 x) {
+    constexpr int A = S / 32, B = S % 32;
+#ifdef __CUDA_ARCH__
+    u32 y0, y1, y2, y3;
+    if (B == 0) {
+        y0 = x.w0; y1 = x.w1; y2 = x.w2; y3 = (u32)((int32_t)x.w2 >> 31);
+    } else {
+        y0 = x.w0 << B;
+        y1 = __funnelshift_l(x.w0, x.w1, B);
+        y2 = __funnelshift_l(x.w1, x.w2, B);
+        y3 = (u32)((int32_t)x.w2 >> (32 - B));
+    }
+    const u32 s3 = (u32)((int32_t)y3 >> 31);
+    gl96 r;
+    if (A == 0) {
+        asm("{\n\t"
+            "sub.cc.u32 %0, %3, %5;\n\t"      // (y0, y1, 0) - y2
+            "subc.cc.u32 %1, %4, 0;\n\t"
+            "subc.u32 %2, 0, 0;\n\t"
+            "add.cc.u32 %1, %1, %5;\n\t"      // + y2 << 32
+            "addc.u32 %2, %2, 0;\n\t"
+            "sub.cc.u32 %0, %0, %6;\n\t"      // - y3 (sign extended)
+            "subc.cc.u32 %1, %1, %7;\n\t"
+            "subc.u32 %2, %2, %7;\n\t"
+            "}"
+            : "=&r"(r.w0), "=&r"(r.w1), "=&r"(r.w2) : "r"(y0), "r"(y1), "r"(y2), "r"(y3), "r"(s3));
+    } else if (A == 1) {
+        asm("{\n\t"
+            "sub.cc.u32 %0, 0, %4;\n\t"       // (0, y0, 0) - y1
+            "subc.cc.u32 %1, %3, 0;\n\t"
+            "subc.u32 %2, 0, 0;\n\t"
+            "sub.cc.u32 %0, %0, %5;\n\t"      // - y2
+            "subc.cc.u32 %1, %1, 0;\n\t"
+            "subc.u32 %2, %2, 0;\n\t"
+            "add.cc.u32 %1, %1, %4;\n\t"      // + y1 << 32
+            "addc.u32 %2, %2, 0;\n\t"
+            "sub.cc.u32 %1, %1, %6;\n\t"      // - y3 << 32 (sign extended)
+            "subc.u32 %2, %2, %7;\n\t"
+            "}"
+            : "=&r"(r.w0), "=&r"(r.w1), "=&r"(r.w2) : "r"(y0), "r"(y1), "r"(y2), "r"(y3), "r"(s3));
+    } else {
+        asm("{\n\t"
+            "sub.cc.u32 %0, 0, %3;\n\t"       // (0, y0, 0) - y0
+            "subc.cc.u32 %1, %3, 0;\n\t"
+            "subc.u32 %2, 0, 0;\n\t"
+            "sub.cc.u32 %0, %0, %4;\n\t"      // - y1
+            "subc.cc.u32 %1, %1, 0;\n\t"
+            "subc.u32 %2, %2, 0;\n\t"
+            "sub.cc.u32 %1, %1, %5;\n\t"      // - y2 << 32
+            "subc.u32 %2, %2, 0;\n\t"
+            "add.cc.u32 %0, %0, %6;\n\t"      // + y3 (sign extended)
+            "addc.cc.u32 %1, %1, %7;\n\t"
+            "addc.u32 %2, %2, %7;\n\t"
+            "sub.cc.u32 %1, %1, %6;\n\t"      // - y3 << 32
+            "subc.u32 %2, %2, %7;\n\t"
+            "}"
+            : "=&r"(r.w0), "=&r"(r.w1), "=&r"(r.w2) : "r"(y0), "r"(y1), "r"(y2), "r"(y3), "r"(s3));
+    }
+    return r;
+#else
+    const l3_i128 Y = l3_val(x) * ((l3_i128)1 << B);
+    const l3_i128 y0 = (u32)Y, y1 = (u32)(Y >> 32), y2 = (u32)(Y >> 64), y3 = (l3_i128)(int32_t)(u32)(Y >> 96);
+    const l3_i128 W = (l3_i128)1 << 32;
+    if (A == 0) return l3_make((y0 - y2 - y3) + W * (y1 + y2));
+    if (A == 1) return l3_make((-y1 - y2) + W * (y0 + y1 - y3));
+    return l3_make((-y0 - y1 + y3) + W * (y0 - y2 - y3));
+#endif
+}
+// some u64 representative of a lazy value with |w2| < 2^30:  (w1:w0) + w2 * (2^32 - 1), one fold of the top limb
+GL_HD u64 l3_reduce(gl96 x) {
+#ifdef __CUDA_ARCH__
+    u32 v0, v1;
+    asm("{\n\t"
+        ".reg .u32 s2, k, tt, hh;\n\t"
+        "shr.s32 s2, %4, 31;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"      // (w0, w1, 0) - w2 (sign extended)
+        "subc.cc.u32 %1, %3, s2;\n\t"
+        "subc.u32 k, 0, s2;\n\t"
+        "add.cc.u32 %1, %1, %4;\n\t"      // + w2 << 32 (sign extended)
+        "addc.u32 k, k, s2;\n\t"
+        "sub.u32 tt, 0, k;\n\t"           // k in {-1, 0, 1}: add k * (2^32 - 1)
+        "shr.s32 hh, k, 1;\n\t"
+        "add.cc.u32 %0, %0, tt;\n\t"
+        "addc.u32 %1, %1, hh;\n\t"
+        "}"
+        : "=&r"(v0), "=&r"(v1) : "r"(x.w0), "r"(x.w1), "r"(x.w2));
+    return ((u64)v1 << 32) | v0;
+#else
+    l3_i128 v = l3_val(x) % (l3_i128)GL_P;
+    if (v < 0) v += (l3_i128)GL_P;
+    return (u64)v;
+#endif
+}
+
+// exponent of 2 of the stage-u twiddle of register m' inside a 16-point DFT (forward: w_16 = 2^156)
+__host__ __device__ constexpr int ntt16_shift(int u, int mp, bool inv) { return (((inv ? 192 - 156 : 156) << (u - 1)) * mp) % 192; }
+__host__ __device__ constexpr int ntt_brev4(int r) { return ((r & 1) << 3) | ((r & 2) << 1) | ((r & 4) >> 1) | ((r & 8) >> 3); }
+
+template <int U, int M, bool INV>
+GL_HD void ntt16_pair(gl96 (&x)[16]) {
+    constexpr int span = 1 << (4 - U);
+    constexpr int S = ntt16_shift(U, M & (span - 1), INV);
+    const gl96 a = x[M], b = x[M + span];
+    x[M] = l3_add(a, b);
+    if (S == 0) x[M + span] = l3_sub(a, b);
+    else if (S == 96) x[M + span] = l3_sub(b, a);
+    else if (S < 96) x[M + span] = l3_shl<(S % 96 == 0 ? 1 : S % 96)>(l3_sub(a, b));
+    else x[M + span] = l3_shl<(S % 96 == 0 ? 1 : S % 96)>(l3_sub(b, a));      // 2^(96 + t) = -2^t
+}
+template <int U, bool INV>
+GL_HD void ntt16_stage(gl96 (&x)[16]) {
+    constexpr int span = 1 << (4 - U);
+    // the 8 butterflies of stage U, registers m with bit `span` clear
+    ntt16_pair<U, (0 / span) * 2 * span + 0 % span, INV>(x);
+    ntt16_pair<U, (1 / span) * 2 * span + 1 % span, INV>(x);
+    ntt16_pair<U, (2 / span) * 2 * span + 2 % span, INV>(x);
+    ntt16_pair<U, (3 / span) * 2 * span + 3 % span, INV>(x);
+    ntt16_pair<U, (4 / span) * 2 * span + 4 % span, INV>(x);
+    ntt16_pair<U, (5 / span) * 2 * span + 5 % span, INV>(x);
+    ntt16_pair<U, (6 / span) * 2 * span + 6 % span, INV>(x);
+    ntt16_pair<U, (7 / span) * 2 * span + 7 % span, INV>(x);
+}
+
+// One radix-16 round (stages t0+1 .. t0+4).  `tw` holds w_P^e for ALL e < P (inverse powers when INV).
+template <bool LAST, bool INV>
+GL_HD void ntt_round16(const NttPass &p, u64 *sm, const u64 *tw, u32 t0, u32 tid, u32 nthreads) {
+    const u32 P = 1u << p.log_p, pitch = ntt_pitch(p.log_p);
+    const u32 blocks_per_lane = P >> 4, log_bpl = p.log_p - 4;
+    const u32 nblocks = blocks_per_lane << p.log_a;
+    const u32 log_js = p.log_p - t0 - 4;
+    const bool linear = (log_js >= 4) || (log_js == 0);
+    const u32 step = log_js >= 4 ? ((1u << log_js) + (1u << (log_js - 4))) : 1u;
+    for (u32 blk = tid; blk < nblocks; blk += nthreads) {
+        const u32 a = blk >> log_bpl, T = blk & (blocks_per_lane - 1);
+        const u32 lo = T & ((1u << log_js) - 1), hi = T >> log_js;
+        const u32 jb = (hi << (p.log_p - t0)) + lo;
+        const u32 base = ntt_sm(pitch, a, jb);
+        gl96 x[16];
+#pragma unroll
+        for (int m = 0; m < 16; m++) x[m] = l3_from(sm[linear ? base + (u32)m * step : ntt_sm(pitch, a, jb + ((u32)m << log_js))]);
+        ntt16_stage<1, INV>(x);
+        ntt16_stage<2, INV>(x);
+        ntt16_stage<3, INV>(x);
+        ntt16_stage<4, INV>(x);
+        const u32 E = lo << t0;   // tau = w_P^E; register r carries tau^bitrev4(r)
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            u64 o = l3_reduce(x[r]);
+            if (!LAST && r != 0) o = gl_mul(o, tw[(u32)ntt_brev4(r) * E]);
+            sm[linear ? base + (u32)r * step : ntt_sm(pitch, a, jb + ((u32)r << log_js))] = o;
+        }
     }
 }
 
@@ -265,15 +482,15 @@ GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nth
 }
 
 // Runs the rounds of one P-point network: remainder round first, radix-16 rounds after, the last one specialised.
-#define NTT_ROUNDS(SYNC)                                                                                        \
+#define NTT_ROUNDS(SYNC, INV)                                                                                        \
     {                                                                                                           \
         u32 t0 = 0;                                                                                             \
         const u32 rem = p.log_p & 3;                                                                            \
         if (rem == 1) { if (p.log_p == 1) ntt_round<1, true>(p, sm, tw, t0, tid, nthreads); else ntt_round<1, false>(p, sm, tw, t0, tid, nthreads); t0 += 1; SYNC; } \
         if (rem == 2) { if (p.log_p == 2) ntt_round<2, true>(p, sm, tw, t0, tid, nthreads); else ntt_round<2, false>(p, sm, tw, t0, tid, nthreads); t0 += 2; SYNC; } \
         if (rem == 3) { if (p.log_p == 3) ntt_round<3, true>(p, sm, tw, t0, tid, nthreads); else ntt_round<3, false>(p, sm, tw, t0, tid, nthreads); t0 += 3; SYNC; } \
-        for (; t0 + 4 < p.log_p; t0 += 4) { ntt_round<4, false>(p, sm, tw, t0, tid, nthreads); SYNC; }          \
-        if (t0 < p.log_p) { ntt_round<4, true>(p, sm, tw, t0, tid, nthreads); SYNC; }                           \
+        for (; t0 + 4 < p.log_p; t0 += 4) { ntt_round16<false, INV>(p, sm, tw, t0, tid, nthreads); SYNC; }      \
+        if (t0 < p.log_p) { ntt_round16<true, INV>(p, sm, tw, t0, tid, nthreads); SYNC; }                       \
     }
 
 #ifdef __CUDACC__
@@ -289,12 +506,12 @@ __global__ void __launch_bounds__(NTT_LB_THREADS, NTT_MINB) ntt_pass_kernel(NttP
     u64 *sm = ntt_smem;
     u64 *tw_s = ntt_smem + (size_t)ntt_pitch(p.log_p) * (1u << p.log_a);   // w_P^e table staged once per CTA
     const u32 tid = threadIdx.x, nthreads = blockDim.x;
-    for (u32 i = tid; i < ((1u << p.log_p) >> 1); i += nthreads) tw_s[i] = p.tw_local[i];
+    for (u32 i = tid; i < (1u << p.log_p); i += nthreads) tw_s[i] = p.tw_local[i];
     const u64 *tw = tw_s;
     for (u64 tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         ntt_load<MODE>(p, sm, tile, tid, nthreads);
         __syncthreads();
-        NTT_ROUNDS(__syncthreads())
+        NTT_ROUNDS(__syncthreads(), (MODE >= NTT_INTT_P1))
         ntt_store<MODE>(p, sm, tile, tid, nthreads);
         __syncthreads();
     }

@@ -24,12 +24,12 @@ struct NttTableStore {
     struct Shift { const u64 *a, *b; };
     std::map<std::tuple<int, int, int>, Shift> shift_cache;
 
-    // w_P^e (inverse: w_P^-e), e < max(P/2, 1)
+    // w_P^e (inverse: w_P^-e), e < P
     const u64 *tw_local(int log_p, bool inverse) {
         auto key = std::make_pair(log_p, (int)inverse);
         auto it = tw_local_cache.find(key);
         if (it != tw_local_cache.end()) return it->second;
-        size_t half = log_p ? (size_t)1 << (log_p - 1) : 1;
+        size_t half = (size_t)1 << log_p;
         std::vector<u64> t(half);
         u64 w = h_gl_root_of_unity(log_p);
         if (inverse) w = h_gl_inv(w);

@@ -31,14 +31,19 @@ template <int R, bool LAST>
 static void replay_round(const NttPass &p, u64 *sm, u32 t0, u32 threads) {
     for (u32 t = 0; t < threads; t++) ntt_round<R, LAST>(p, sm, p.tw_local, t0, t, threads);
 }
+template <bool LAST, bool INV>
+static void replay_round16(const NttPass &p, u64 *sm, u32 t0, u32 threads) {
+    for (u32 t = 0; t < threads; t++) ntt_round16<LAST, INV>(p, sm, p.tw_local, t0, t, threads);
+}
+template <bool INV>
 static void replay_rounds(const NttPass &p, u64 *sm, u32 threads) {
     u32 t0 = 0;
     const u32 rem = p.log_p & 3;
     if (rem == 1) { if (p.log_p == 1) replay_round<1, true>(p, sm, t0, threads); else replay_round<1, false>(p, sm, t0, threads); t0 += 1; }
     if (rem == 2) { if (p.log_p == 2) replay_round<2, true>(p, sm, t0, threads); else replay_round<2, false>(p, sm, t0, threads); t0 += 2; }
     if (rem == 3) { if (p.log_p == 3) replay_round<3, true>(p, sm, t0, threads); else replay_round<3, false>(p, sm, t0, threads); t0 += 3; }
-    for (; t0 + 4 < p.log_p; t0 += 4) replay_round<4, false>(p, sm, t0, threads);
-    if (t0 < p.log_p) replay_round<4, true>(p, sm, t0, threads);
+    for (; t0 + 4 < p.log_p; t0 += 4) replay_round16<false, INV>(p, sm, t0, threads);
+    if (t0 < p.log_p) replay_round16<true, INV>(p, sm, t0, threads);
 }
 
 template <int MODE>
@@ -48,7 +53,7 @@ static void replay_mode(const NttLaunch &l, u64 grid) {
     for (u64 bid = 0; bid < grid; bid++) {
         for (u64 tile = bid; tile < p.num_tiles; tile += grid) {
             for (u32 t = 0; t < l.threads; t++) ntt_load<MODE>(p, sm.data(), tile, t, l.threads);
-            replay_rounds(p, sm.data(), l.threads);
+            replay_rounds<(MODE >= NTT_INTT_P1)>(p, sm.data(), l.threads);
             for (u32 t = 0; t < l.threads; t++) ntt_store<MODE>(p, sm.data(), tile, t, l.threads);
         }
     }
