@@ -248,8 +248,11 @@ def main():
 
     def step_e2e():
         if distributed:
-            staged = host.cuda(non_blocking=True)          # H2D of this rank's columns
-            b = E.ShardedPolynomialBatch.from_values(staged, plan, rank, exchange=exchange)
+            if exchange is not None:                       # host columns straight into the copy / transform / peer-store pipeline
+                b = E.ShardedPolynomialBatch.from_values(host_cols, plan, rank, exchange=exchange)
+            else:
+                staged = host.cuda(non_blocking=True)      # H2D of this rank's columns
+                b = E.ShardedPolynomialBatch.from_values(staged, plan, rank)
             return b.cap                                   # replicated cap, already on the host
         b = E.PolynomialBatch.from_values(host_cols, RATE_BITS, False, CAP_HEIGHT)
         cap = b.merkle_tree.cap            # D2H read of the result

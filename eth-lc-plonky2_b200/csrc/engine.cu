@@ -664,6 +664,48 @@ eng_status eng_lde_peer_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_
     return ENG_OK;
 }
 
+// Same with HOST columns: the copy / iNTT / LDE pipeline of make_batch, chunk by chunk, with the fused peer stores.
+eng_status eng_lde_peer_host(const uint64_t *const *cols_host, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits,
+                             int32_t is_values, uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *scratch_dev,
+                             uint64_t *const *shard_out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!cols_host || !coeffs_out_dev || !scratch_dev || !shard_out) return fail(ENG_ERR_INVALID, "NULL buffer");
+    if (num_polys == 0) return fail(ENG_ERR_INVALID, "no polynomials");
+    if (log_n > 2 * NTT_MAX_LOGP || log_n + rate_bits > 32) return fail(ENG_ERR_INVALID, "size unsupported");
+    const u32 G = 1u << log_row_shards;
+    if (G > NTT_MAX_SHARDS) return fail(ENG_ERR_INVALID, "more than %d row shards", NTT_MAX_SHARDS);
+    for (u32 gi = 0; gi < G; gi++)
+        if (!shard_out[gi]) return fail(ENG_ERR_INVALID, "shard_out[%u] is NULL", gi);
+    for (u32 c = 0; c < num_polys; c++)
+        if (!cols_host[c]) return fail(ENG_ERR_INVALID, "column %u is NULL", c);
+    const u64 n = (u64)1 << log_n, L = n << rate_bits, rows_per_shard = L >> log_row_shards;
+    u64 per = env_bytes("ENG_H2D_CHUNK_BYTES", (size_t)32 << 20) / (n * sizeof(u64));
+    const u32 chunk = (u32)(per < 1 ? 1 : (per > num_polys ? num_polys : per));
+    CU(cudaEventRecord(g.fork_ev, g.stream));
+    CU(cudaStreamWaitEvent(g.copy_stream, g.fork_ev, 0));
+    std::vector<NttLaunch> plan;
+    for (u32 c0 = 0; c0 < num_polys; c0 += chunk) {
+        const u32 cc = num_polys - c0 < chunk ? num_polys - c0 : chunk;
+        u64 *co = coeffs_out_dev + (size_t)c0 * n, *sc = scratch_dev + (size_t)c0 * L;
+        ST(h2d_columns(cols_host + c0, cc, n, co));
+        CU(cudaEventRecord(g.chunk_ev, g.copy_stream));
+        CU(cudaStreamWaitEvent(g.stream, g.chunk_ev, 0));
+        if (is_values) {
+            plan.clear();
+            if (!ntt_plan_intt(g.tables, co, n, sc, n, co, n, cc, log_n, plan)) return fail(ENG_ERR_INVALID, "iNTT size unsupported");
+            ST(launch_plan(plan));
+        }
+        u64 *so[NTT_MAX_SHARDS];
+        for (u32 gi = 0; gi < G; gi++) so[gi] = shard_out[gi] + (size_t)c0 * rows_per_shard;
+        plan.clear();
+        if (!ntt_plan_lde(g.tables, co, n, sc, cc, log_n, rate_bits, log_row_shards, plan, so))
+            return fail(ENG_ERR_INVALID, "LDE shape unsupported (log_n=%u rate_bits=%u log_row_shards=%u)", log_n, rate_bits, log_row_shards);
+        ST(launch_plan(plan));
+    }
+    return ENG_OK;
+}
+
 // Exchange buffers live outside the stream-ordered pool (cudaMalloc) so that they can be exported over CUDA IPC.
 eng_status eng_peer_buffer_alloc(uint64_t num_elems, uint64_t **dev_out, uint8_t handle_out[64]) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);

@@ -166,11 +166,20 @@ class ShardedPolynomialBatch:
         same plan) the column->row exchange is fused into the LDE's last pass; its leaf matrix is reused by every call."""
         if dist is None:
             import torch.distributed as dist
-        if ops is None:
+        if ops is None and not isinstance(local_values, (list, tuple)):
             ops = EngineOps(local_values.device)
         n = 1 << plan.log_n
         c_r = plan.col_counts[rank]
-        if tuple(local_values.shape) != (c_r, n):
+        host_cols = None
+        if isinstance(local_values, (list, tuple)):       # host columns (numpy uint64): only with the fused exchange
+            if exchange is None or plan.world == 1:
+                raise EngineError(_lib.ENG_ERR_INVALID, "host columns need exchange= (PeerExchange) and world > 1")
+            host_cols = [np.ascontiguousarray(c, dtype=np.uint64) for c in local_values]
+            if len(host_cols) != c_r or any(c.shape != (n,) for c in host_cols):
+                raise EngineError(_lib.ENG_ERR_INVALID, "rank %d expects %d host columns of %d elements" % (rank, c_r, n))
+            if ops is None:
+                ops = EngineOps(exchange.recv.device)
+        elif tuple(local_values.shape) != (c_r, n):
             raise EngineError(_lib.ENG_ERR_INVALID, "rank %d expects a [%d][%d] column shard, got %s" % (rank, c_r, n, tuple(local_values.shape)))
         coeffs = ops.empty(c_r * n).view(c_r, n)
         if exchange is not None and plan.world > 1:
@@ -180,9 +189,14 @@ class ShardedPolynomialBatch:
             scratch = ops.empty(c_r * (n << plan.rate_bits))
             exchange.barrier()                       # every rank has finished reading its leaf matrix of the previous call
             t1 = time.perf_counter()
-            check(_lib.lib().eng_lde_peer_dev(C.c_void_p(local_values.data_ptr()), c_r, plan.log_n, plan.rate_bits, int(is_values),
-                                              plan.log_world, C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()),
-                                              exchange.shard_out))
+            if host_cols is not None:
+                ptrs = (C.c_void_p * c_r)(*[c.ctypes.data for c in host_cols])
+                check(_lib.lib().eng_lde_peer_host(ptrs, c_r, plan.log_n, plan.rate_bits, int(is_values), plan.log_world,
+                                                   C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), exchange.shard_out))
+            else:
+                check(_lib.lib().eng_lde_peer_dev(C.c_void_p(local_values.data_ptr()), c_r, plan.log_n, plan.rate_bits, int(is_values),
+                                                  plan.log_world, C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                                  exchange.shard_out))
             _lib.synchronize()
             t2 = time.perf_counter()
             exchange.barrier()                       # every rank's stores have landed

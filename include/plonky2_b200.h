@@ -92,6 +92,11 @@ eng_status eng_lde_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_t log
  * (stream sync + barrier) before hashing the received rows.  log_row_shards <= 4. */
 eng_status eng_lde_peer_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits, int32_t is_values,
                             uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *scratch_dev, uint64_t *const *shard_out);
+/* Same from HOST columns (pinned or pageable): column chunks are copied on a second stream while the previous chunk runs
+ * its iNTT and LDE, as in eng_batch_from_values. */
+eng_status eng_lde_peer_host(const uint64_t *const *cols_host, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits,
+                             int32_t is_values, uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *scratch_dev,
+                             uint64_t *const *shard_out);
 /* Exchange buffers: device memory outside the stream-ordered pool, exportable to the other ranks of the box through a
  * 64-byte CUDA IPC handle (cudaIpcGetMemHandle / cudaIpcOpenMemHandle). */
 eng_status eng_peer_buffer_alloc(uint64_t num_elems, uint64_t **dev_out, uint8_t handle_out[64]);

@@ -274,7 +274,7 @@ def test_row_sharded_path_emulated_on_one_gpu(engine, oracle, world):
 
 
 @pytest.mark.parametrize("world,log_n", [(2, 13), (4, 13), (8, 15), (2, 9), (16, 14)])
-def test_fused_exchange_stores_emulated_on_one_gpu(engine, oracle, world, log_n):
+def test_fused_exchange_stores_emulated_on_one_gpu(engine, oracle, world, log_n, monkeypatch):
     """eng_lde_peer_dev: the LDE's last pass stores row shard g through shard_out[g].  Here the 'peer' leaf matrices are
     ordinary local buffers (one per emulated rank), so the store addressing of the fused exchange is checked without
     CUDA IPC; the real peer mappings are exercised by bench.py --gpus N (its cap must equal the NCCL path's)."""
@@ -294,8 +294,15 @@ def test_fused_exchange_stores_emulated_on_one_gpu(engine, oracle, world, log_n)
         coeffs = ops.empty(len(cols) << log_n).view(len(cols), 1 << log_n)
         scratch = ops.empty(len(cols) << (log_n + r))
         shard_out = (C.c_void_p * world)(*[m.data_ptr() + plan.col_offsets[rank] * plan.rows_per_rank * 8 for m in mats])
-        check(lib().eng_lde_peer_dev(C.c_void_p(local.data_ptr()), len(cols), log_n, r, 1, plan.log_world,
-                                     C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), shard_out))
+        if rank % 2 == 0:
+            check(lib().eng_lde_peer_dev(C.c_void_p(local.data_ptr()), len(cols), log_n, r, 1, plan.log_world,
+                                         C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), shard_out))
+        else:   # odd ranks: host columns through the chunked copy / transform / peer-store pipeline (2 columns per chunk)
+            monkeypatch.setenv("ENG_H2D_CHUNK_BYTES", str(2 * (8 << log_n)))
+            hc = [vals[c].copy() for c in cols]
+            ptrs = (C.c_void_p * len(hc))(*[c.ctypes.data for c in hc])
+            check(lib().eng_lde_peer_host(ptrs, len(cols), log_n, r, 1, plan.log_world,
+                                          C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), shard_out))
         synchronize()
         assert (ops.to_numpy(coeffs) == ref.coeffs[cols.start:cols.stop]).all()
     caps = []
