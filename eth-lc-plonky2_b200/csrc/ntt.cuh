@@ -82,10 +82,15 @@ GL_HD u64 ntt_twiddle2(const NttPass &p, u64 e) {
 }
 
 // ---- phase 1: global -> shared ----
+// Loads are issued NTT_LOAD_BATCH at a time before the first one is consumed (the phase is DRAM/L2 latency).
+#ifndef NTT_LOAD_BATCH
+#define NTT_LOAD_BATCH 4
+#endif
 template <int MODE>
 GL_HD void ntt_load(const NttPass &p, u64 *sm, u64 tile, u32 tid, u32 nthreads) {
     const u32 P = 1u << p.log_p, A = 1u << p.log_a, pitch = ntt_pitch(p.log_p);
     const u32 total = P << p.log_a;
+    constexpr int B = NTT_LOAD_BATCH;
     if (MODE == NTT_LDE_FIRST || MODE == NTT_INTT_P1 || MODE == NTT_INTT_P2) {
         // strided tile: element (j, a) = in[col][j*st + r0 + a]
         const u32 log_st = p.log_n - p.log_p;
@@ -96,12 +101,27 @@ GL_HD void ntt_load(const NttPass &p, u64 *sm, u64 tile, u32 tid, u32 nthreads) 
         u32 e = 0;
         if (MODE == NTT_LDE_FIRST) { e = (u32)(rem & ((1u << p.rate_bits) - 1)); rem >>= p.rate_bits; }
         const u64 r0 = rem << p.log_a;
-        const u64 *src = p.in + col * p.in_col_stride;
-        for (u32 idx = tid; idx < total; idx += nthreads) {
-            u32 a = idx & (A - 1), j = idx >> p.log_a;
-            u64 v = src[((u64)j << log_st) + r0 + a];
-            if (MODE == NTT_LDE_FIRST) v = gl_mul(v, p.shift_a[((u64)e << p.log_p) + j]);  // s_e^(j*st); s_e^r at the store
-            sm[ntt_sm(pitch, a, j)] = v;
+        const u64 *src = p.in + col * p.in_col_stride + r0;
+        const u64 *sh = (MODE == NTT_LDE_FIRST) ? p.shift_a + ((u64)e << p.log_p) : nullptr;
+        for (u32 i0 = tid; i0 < total; i0 += nthreads * B) {
+            u64 v[B], w[B];
+#pragma unroll
+            for (int k = 0; k < B; k++) {
+                const u32 idx = i0 + (u32)k * nthreads;
+                if (idx < total) {
+                    const u32 a = idx & (A - 1), j = idx >> p.log_a;
+                    v[k] = src[((u64)j << log_st) + a];
+                    if (MODE == NTT_LDE_FIRST) w[k] = sh[j];   // s_e^(j*st); s_e^r at the store
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < B; k++) {
+                const u32 idx = i0 + (u32)k * nthreads;
+                if (idx < total) {
+                    const u32 a = idx & (A - 1), j = idx >> p.log_a;
+                    sm[ntt_sm(pitch, a, j)] = (MODE == NTT_LDE_FIRST) ? gl_mul(v[k], w[k]) : v[k];
+                }
+            }
         }
     } else if (MODE == NTT_LDE_SINGLE) {
         // lane = (col, e); element j = coeffs[col][j] * s_e^j
@@ -116,17 +136,28 @@ GL_HD void ntt_load(const NttPass &p, u64 *sm, u64 tile, u32 tid, u32 nthreads) 
         }
     } else {
         // NTT_DIF_LAST / NTT_INTT_SINGLE: lane a = a-th consecutive run of P contiguous elements
-        for (u32 idx = tid; idx < total; idx += nthreads) {
-            u32 j = idx & (P - 1), a = idx >> p.log_p;
-            u64 unit = tile * A + a;
-            u64 v = 0;
-            if (MODE == NTT_DIF_LAST) {
-                // the LDE buffer is one contiguous array of aligned P-point runs, whatever its shard layout
-                if (unit < p.num_units) v = p.in[(unit << p.log_p) + j];
-            } else {
-                if (unit < p.num_cols) v = p.in[unit * p.in_col_stride + j];
+        for (u32 i0 = tid; i0 < total; i0 += nthreads * B) {
+            u64 v[B];
+#pragma unroll
+            for (int k = 0; k < B; k++) {
+                const u32 idx = i0 + (u32)k * nthreads;
+                v[k] = 0;
+                if (idx < total) {
+                    const u32 j = idx & (P - 1), a = idx >> p.log_p;
+                    const u64 unit = tile * A + a;
+                    if (MODE == NTT_DIF_LAST) {
+                        // the LDE buffer is one contiguous array of aligned P-point runs, whatever its shard layout
+                        if (unit < p.num_units) v[k] = p.in[(unit << p.log_p) + j];
+                    } else {
+                        if (unit < p.num_cols) v[k] = p.in[unit * p.in_col_stride + j];
+                    }
+                }
             }
-            sm[ntt_sm(pitch, a, j)] = v;
+#pragma unroll
+            for (int k = 0; k < B; k++) {
+                const u32 idx = i0 + (u32)k * nthreads;
+                if (idx < total) sm[ntt_sm(pitch, idx >> p.log_p, idx & (P - 1))] = v[k];
+            }
         }
     }
 }
