@@ -32,9 +32,9 @@ RATE_BITS = 3
 CAP_HEIGHT = 4
 IMAD_PER_PERM = 6612
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures at configs[1]
-# (profiles/r01_leaves_v1.md, profiles/r01_ntt_v2.md); only quoted when the workload is that configuration
+# (profiles/r01_leaves_v1.md, profiles/r01_ntt_v3.md); only quoted when the workload is that configuration
 NCU_TRAFFIC_LEAVES = 9.086e9 + 0.330e9
-NCU_TRAFFIC_NTT = (1.74 + 9.23 + 9.06 + 9.24) * 1e9 + 4 * 1.13e9
+NCU_TRAFFIC_NTT = (1.14 + 1.11 + 1.14 + 1.11 + 1.57 + 9.64 + 9.06 + 9.03) * 1e9
 NOMINAL_IMAD_PER_S = 148 * 64 * 1.965e9   # 64 IMAD/clk/SM; no integer entry in MEASURED_PEAKS.json
 
 
@@ -349,8 +349,8 @@ def main():
             "roofline_hbm": {"kernel": "ntt_pass_kernel x4 (iNTT 2 passes + coset LDE 2 passes)", "bound": "hbm",
                              "achieved": hbm_rate, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_rate / peaks["hbm_gbs"],
                              "traffic": NCU_TRAFFIC_NTT if (cols, log_n) == (135, 20) else None, "peak_kind": peak_kind,
-                             "note": "integer-issue bound, not HBM bound: ~40 alu instructions per butterfly on the half-rate alu pipe "
-                                     "(profiles/r01_ntt_v2.md); reported against the HBM roof because BASELINE.json asks for it", "kernel_ms": ntt_ms, "algorithmic_bytes": b_ntt(cols, n)},
+                             "note": "integer-issue bound, not HBM bound: alu pipe 57-69 % of peak at 54-61 % issue activity, DRAM 7-16 % "
+                                     "(profiles/r01_ntt_v3.md); reported against the HBM roof because BASELINE.json asks for it", "kernel_ms": ntt_ms, "algorithmic_bytes": b_ntt(cols, n)},
             "clocks": clocks,
             "cap0": "%016x" % int(cap_e2e[0][0]),
         }
