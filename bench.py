@@ -89,8 +89,8 @@ class ClockSampler(threading.Thread):
 def cpu_commit(cols, log_n, threads=None):
     """Times the CPU oracle on one commit; returns (seconds, stage dict, threads)."""
     from oracle import oracle as O
-    if threads:
-        O.lib().orc_set_num_threads(threads)
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    O.lib().orc_set_num_threads(threads or os.cpu_count() or 1)
     vals = O.splitmix_columns(cols, 1 << log_n)
     t0 = time.perf_counter()
     b = O.Batch.from_values(vals, RATE_BITS, CAP_HEIGHT)
