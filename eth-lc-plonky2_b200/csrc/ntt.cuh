@@ -136,6 +136,34 @@ GL_HD void ntt_load(const NttPass &p, u64 *sm, u64 tile, u32 tid, u32 nthreads) 
         }
     } else {
         // NTT_DIF_LAST / NTT_INTT_SINGLE: lane a = a-th consecutive run of P contiguous elements
+#ifdef __CUDA_ARCH__
+        if (MODE == NTT_DIF_LAST && p.log_p >= 1) {
+            // 16-byte accesses: element pairs (j, j+1), j even
+            const u32 pairs = total >> 1;
+            for (u32 i0 = tid; i0 < pairs; i0 += nthreads * B) {
+                ulonglong2 v[B];
+#pragma unroll
+                for (int k = 0; k < B; k++) {
+                    const u32 idx = (i0 + (u32)k * nthreads) << 1;
+                    v[k] = make_ulonglong2(0, 0);
+                    if (idx < total) {
+                        const u64 unit = tile * A + (idx >> p.log_p);
+                        if (unit < p.num_units) v[k] = *reinterpret_cast<const ulonglong2 *>(p.in + (unit << p.log_p) + (idx & (P - 1)));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < B; k++) {
+                    const u32 idx = (i0 + (u32)k * nthreads) << 1;
+                    if (idx < total) {
+                        const u32 a = idx >> p.log_p, j = idx & (P - 1);
+                        sm[ntt_sm(pitch, a, j)] = v[k].x;
+                        sm[ntt_sm(pitch, a, j + 1)] = v[k].y;
+                    }
+                }
+            }
+            return;
+        }
+#endif
         for (u32 i0 = tid; i0 < total; i0 += nthreads * B) {
             u64 v[B];
 #pragma unroll
@@ -465,6 +493,21 @@ GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nth
             }
         }
     } else if (MODE == NTT_DIF_LAST) {
+#ifdef __CUDA_ARCH__
+        if (p.log_p >= 1) {
+            for (u32 idx = tid << 1; idx < total; idx += nthreads << 1) {   // 16-byte stores: pairs (q, q+1), q even
+                const u32 q = idx & (P - 1), a = idx >> p.log_p;
+                const u64 unit = tile * A + a;
+                if (unit < p.num_units) {
+                    const u64 i0 = unit << p.log_p;
+                    u64 *dst = p.num_shard_ptrs ? p.shard_out[i0 / p.shard_stride] + i0 % p.shard_stride : p.out + i0;
+                    *reinterpret_cast<ulonglong2 *>(dst + q) =
+                        make_ulonglong2(gl_canon(sm[ntt_sm(pitch, a, q)]), gl_canon(sm[ntt_sm(pitch, a, q + 1)]));
+                }
+            }
+            return;
+        }
+#endif
         for (u32 idx = tid; idx < total; idx += nthreads) {
             u32 q = idx & (P - 1), a = idx >> p.log_p;
             u64 unit = tile * A + a;
