@@ -100,3 +100,13 @@ def test_shard_plan():
         E.ShardPlan(135, 20, 3, 2, 8)        # 8 ranks cannot own whole sub-trees of a 4-entry cap
     with pytest.raises(E.EngineError):
         E.ShardPlan(135, 20, 3, 4, 3)        # not a power of two
+
+
+def test_host_columns_need_the_fused_exchange():
+    """ShardedPolynomialBatch.from_values accepts HOST columns only together with a PeerExchange (the chunked copy /
+    transform / peer-store pipeline); without one it refuses instead of silently staging through another path."""
+    import eth_lc_plonky2_b200 as E
+    plan = E.ShardPlan(6, 4, 1, 1, 2)
+    cols = [np.zeros(16, np.uint64) for _ in range(3)]
+    with pytest.raises(E.EngineError):
+        E.ShardedPolynomialBatch.from_values(cols, plan, 0, dist=object(), ops=OracleOps())
