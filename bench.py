@@ -342,6 +342,9 @@ def main():
                          "unit": "TIMAD32/s", "frac": imad_rate / NOMINAL_IMAD_PER_S,
                          "traffic": NCU_TRAFFIC_LEAVES if (cols, log_n) == (135, 20) else None,
                          "hbm_floor_ms": (8 * cols * L + 32 * L) / (peaks["hbm_gbs"] * 1e9) * 1e3,
+                         # the same kernel against the HBM roof (it is not memory bound: one leaf is 1080 B and 17 permutations)
+                         "hbm": {"bound": "hbm", "achieved": (8 * cols * L + 32 * L) / (leaf_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                 "unit": "GB/s", "frac": (8 * cols * L + 32 * L) / (leaf_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                          "peak_kind": "nominal 148 SM x 64 IMAD/clk x 1.965 GHz (no measured integer peak in MEASURED_PEAKS.json)",
                          "perms_per_s": leaf_perms / (leaf_ms * 1e-3), "kernel_ms": leaf_ms,
                          "measured_issue_rates_Tops": {k: v / 1e12 for k, v in int_peak.items()},
