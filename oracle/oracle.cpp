@@ -98,6 +98,14 @@ static OrcFriParams parse_params(const int *p) {
     for (int i = 0; i < p[5]; i++) P.arity_bits.push_back(p[6 + i]);
     return P;
 }
+// Horner evaluation of one coefficient vector at a base-field point (PolynomialCoeffs::eval); used by the size-independent
+// property tests at sizes where a whole oracle commit would take minutes
+u64 orc_poly_eval(const u64 *coeffs, u64 n, u64 x) {
+    u64 acc = 0;
+    x = gl_canon(x);
+    for (u64 i = n; i-- > 0;) acc = gl_add(gl_mul(acc, x), gl_canon(coeffs[i]));
+    return gl_canon(acc);
+}
 void orc_batch_eval_c(void *h, const u64 *z, u64 *out) {
     vec2 v = orc_batch_eval(*(OrcBatch *)h, gl2_make(gl_canon(z[0]), gl_canon(z[1])));
     for (size_t i = 0; i < v.size(); i++) { out[2 * i] = v[i].a; out[2 * i + 1] = v[i].b; }

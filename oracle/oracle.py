@@ -226,6 +226,15 @@ class Challenger:
             lib().orc_challenger_free(self.h); self.h = None
 
 
+def poly_eval_base(coeffs, x):
+    """PolynomialCoeffs::eval at a base-field point (Horner), canonical result."""
+    c = np.ascontiguousarray(coeffs, dtype=np.uint64)
+    f = lib().orc_poly_eval
+    f.argtypes = [_u64p, C.c_uint64, C.c_uint64]
+    f.restype = C.c_uint64
+    return int(f(c, c.shape[0], int(x)))
+
+
 def batch_eval(batch, z):
     """eval_commitment(z, batch): every polynomial of the batch at z in F_p^2 -> [C][2]."""
     out = np.zeros((batch.C, 2), np.uint64)

@@ -312,3 +312,38 @@ def test_fused_exchange_stores_emulated_on_one_gpu(engine, oracle, world, log_n,
         assert (got.T == ref.leaves[lo:lo + plan.rows_per_rank]).all()
         caps.append(ops.merkle(mats[g], C_, plan.rows_per_rank, plan.local_cap_height).cap)
     assert (np.concatenate(caps) == ref.cap).all()
+
+
+@pytest.mark.parametrize("log_n", [25, 26])
+def test_maximum_sizes_properties(engine, oracle, log_n):
+    """The largest transforms the planner supports (2^25 and 2^26 rows: 2^13-point passes, one CTA per SM, the twiddle
+    table at its largest).  The oracle would take minutes at this size, so the check is by properties: coefficients
+    interpolate the values (oracle Horner at sampled subgroup points), LDE rows are evaluations on the coset in
+    bit-reversed order, Merkle paths verify against the cap."""
+    import torch
+    rng = np.random.default_rng(log_n)
+    C_, r, h = 2, 1, 4
+    n = 1 << log_n
+    L = n << r
+    vals = rand_field(rng, (C_, n), noncanonical=True)
+    t = torch.from_numpy(vals.view(np.int64)).cuda()
+    b = engine.PolynomialBatch.from_values(t, r, False, h)
+    co = b.polynomials
+    assert (co < np.uint64(P)).all()
+    wn = pow(1753635133440165772, 1 << (32 - log_n), P)
+    wl = pow(1753635133440165772, 1 << (32 - log_n - r), P)
+
+    def ev(c, x):
+        return int(oracle.poly_eval_base(co[c], x))
+
+    for c in range(C_):
+        for i in (0, 1, n - 1, int(rng.integers(n))):
+            assert ev(c, pow(wn, i, P)) == int(vals[c][i]) % P
+    cap = b.merkle_tree.cap
+    for k in (0, L - 1, int(rng.integers(L))):
+        row = b.merkle_tree.get(k)
+        x = 7 * pow(wl, bitrev(k, log_n + r), P) % P
+        for c in range(C_):
+            assert int(row[c]) == ev(c, x)
+        assert oracle.merkle_verify(row, k, cap, b.merkle_tree.prove(k))
+    b.close()
