@@ -639,7 +639,8 @@ eng_status eng_lde_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_t log
 
 // ---- fused exchange: the LDE's last pass stores straight into the row-shard owners' leaf matrices (NVLink P2P) ----
 eng_status eng_lde_peer_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits, int32_t is_values,
-                            uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *scratch_dev, uint64_t *const *shard_out) {
+                            uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *scratch_dev, uint64_t *const *shard_out,
+                            uint32_t first_shard) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     ST(check_ready());
     if (!src_dev || !coeffs_out_dev || !scratch_dev || !shard_out) return fail(ENG_ERR_INVALID, "NULL buffer");
@@ -658,7 +659,7 @@ eng_status eng_lde_peer_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_
         CU(cudaMemcpyAsync(coeffs_out_dev, src_dev, (size_t)num_polys * n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
     }
     plan.clear();
-    if (!ntt_plan_lde(g.tables, coeffs_out_dev, n, scratch_dev, num_polys, log_n, rate_bits, log_row_shards, plan, shard_out))
+    if (!ntt_plan_lde(g.tables, coeffs_out_dev, n, scratch_dev, num_polys, log_n, rate_bits, log_row_shards, plan, shard_out, first_shard))
         return fail(ENG_ERR_INVALID, "LDE shape unsupported (log_n=%u rate_bits=%u log_row_shards=%u)", log_n, rate_bits, log_row_shards);
     ST(launch_plan(plan));
     return ENG_OK;
@@ -667,7 +668,7 @@ eng_status eng_lde_peer_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_
 // Same with HOST columns: the copy / iNTT / LDE pipeline of make_batch, chunk by chunk, with the fused peer stores.
 eng_status eng_lde_peer_host(const uint64_t *const *cols_host, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits,
                              int32_t is_values, uint32_t log_row_shards, uint64_t *coeffs_out_dev, uint64_t *scratch_dev,
-                             uint64_t *const *shard_out) {
+                             uint64_t *const *shard_out, uint32_t first_shard) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     ST(check_ready());
     if (!cols_host || !coeffs_out_dev || !scratch_dev || !shard_out) return fail(ENG_ERR_INVALID, "NULL buffer");
@@ -699,7 +700,7 @@ eng_status eng_lde_peer_host(const uint64_t *const *cols_host, uint32_t num_poly
         u64 *so[NTT_MAX_SHARDS];
         for (u32 gi = 0; gi < G; gi++) so[gi] = shard_out[gi] + (size_t)c0 * rows_per_shard;
         plan.clear();
-        if (!ntt_plan_lde(g.tables, co, n, sc, cc, log_n, rate_bits, log_row_shards, plan, so))
+        if (!ntt_plan_lde(g.tables, co, n, sc, cc, log_n, rate_bits, log_row_shards, plan, so, first_shard))
             return fail(ENG_ERR_INVALID, "LDE shape unsupported (log_n=%u rate_bits=%u log_row_shards=%u)", log_n, rate_bits, log_row_shards);
         ST(launch_plan(plan));
     }

@@ -52,6 +52,9 @@ struct NttPass {
     // rank's [C_r][L/G] block lives inside row-shard owner g's [C][L/G] leaf matrix, so the all-to-all is the store.
     u32 num_shard_ptrs;
     u64 *shard_out[NTT_MAX_SHARDS];
+    // fused exchange: the last pass walks its tiles starting at tile_rot (= this rank's own row shard), so that at any
+    // moment the G ranks of the box store into G DIFFERENT destinations instead of all hammering shard 0, then 1, ...
+    u64 tile_rot;
     const u64 *tw_local;  // w_P^e (or inverse), e < P
     const u64 *w_lo, *w_hi;  // w_n^e = w_hi[e >> w_lo_bits] * w_lo[e & mask]   (or inverse powers)
     u32 w_lo_bits;
@@ -582,7 +585,9 @@ __global__ void __launch_bounds__(NTT_LB_THREADS, NTT_MINB) ntt_pass_kernel(NttP
     const u32 tid = threadIdx.x, nthreads = blockDim.x;
     for (u32 i = tid; i < (1u << p.log_p); i += nthreads) tw_s[i] = p.tw_local[i];
     const u64 *tw = tw_s;
-    for (u64 tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (u64 tile_i = blockIdx.x; tile_i < p.num_tiles; tile_i += gridDim.x) {
+        u64 tile = tile_i + p.tile_rot;
+        if (tile >= p.num_tiles) tile -= p.num_tiles;
         ntt_load<MODE>(p, sm, tile, tid, nthreads);
         __syncthreads();
         NTT_ROUNDS(__syncthreads(), (MODE >= NTT_INTT_P1))

@@ -148,8 +148,10 @@ static inline bool ntt_plan_intt(NttTableStore &ts, const u64 *in, u64 in_stride
 // (log_shards = 0: the plain [C][L] layout).  Returns false if the shape is unsupported.
 // shard_out (optional, 2^log_shards pointers): the last pass stores row shard g at shard_out[g] ([C][L/G], possibly
 // peer memory) instead of lde + g * C * L/G; lde is then only the local intermediate of the first pass.
+// first_shard: with shard_out, the last pass starts at that row shard (the caller's own rank) and wraps around.
 static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs_stride, u64 *lde, u32 C, u32 log_n,
-                                u32 rate_bits, u32 log_shards, std::vector<NttLaunch> &plan, u64 *const *shard_out = nullptr) {
+                                u32 rate_bits, u32 log_shards, std::vector<NttLaunch> &plan, u64 *const *shard_out = nullptr,
+                                u32 first_shard = 0) {
     if (log_n > 2 * NTT_MAX_LOGP) return false;
     const u32 log_l = log_n + rate_bits;
     if (log_shards > log_l) return false;
@@ -194,6 +196,8 @@ static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs
     p.num_tiles = (units + (1u << p.log_a) - 1) >> p.log_a;
     p.tw_local = ts.tw_local(lst, false);
     set_shard_ptrs(p);
+    if (shard_out && (p.num_tiles % ((u64)1 << log_shards)) == 0)
+        p.tile_rot = (p.num_tiles >> log_shards) * (first_shard & ((1u << log_shards) - 1));
     plan.push_back(ntt_make_launch(NTT_DIF_LAST, p));
     return true;
 }

@@ -192,11 +192,11 @@ class ShardedPolynomialBatch:
             if host_cols is not None:
                 ptrs = (C.c_void_p * c_r)(*[c.ctypes.data for c in host_cols])
                 check(_lib.lib().eng_lde_peer_host(ptrs, c_r, plan.log_n, plan.rate_bits, int(is_values), plan.log_world,
-                                                   C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), exchange.shard_out))
+                                                   C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), exchange.shard_out, rank))
             else:
                 check(_lib.lib().eng_lde_peer_dev(C.c_void_p(local_values.data_ptr()), c_r, plan.log_n, plan.rate_bits, int(is_values),
                                                   plan.log_world, C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()),
-                                                  exchange.shard_out))
+                                                  exchange.shard_out, rank))
             _lib.synchronize()
             t2 = time.perf_counter()
             exchange.barrier()                       # every rank's stores have landed

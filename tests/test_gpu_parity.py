@@ -296,13 +296,13 @@ def test_fused_exchange_stores_emulated_on_one_gpu(engine, oracle, world, log_n,
         shard_out = (C.c_void_p * world)(*[m.data_ptr() + plan.col_offsets[rank] * plan.rows_per_rank * 8 for m in mats])
         if rank % 2 == 0:
             check(lib().eng_lde_peer_dev(C.c_void_p(local.data_ptr()), len(cols), log_n, r, 1, plan.log_world,
-                                         C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), shard_out))
+                                         C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), shard_out, rank))
         else:   # odd ranks: host columns through the chunked copy / transform / peer-store pipeline (2 columns per chunk)
             monkeypatch.setenv("ENG_H2D_CHUNK_BYTES", str(2 * (8 << log_n)))
             hc = [vals[c].copy() for c in cols]
             ptrs = (C.c_void_p * len(hc))(*[c.ctypes.data for c in hc])
             check(lib().eng_lde_peer_host(ptrs, len(cols), log_n, r, 1, plan.log_world,
-                                          C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), shard_out))
+                                          C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), shard_out, rank))
         synchronize()
         assert (ops.to_numpy(coeffs) == ref.coeffs[cols.start:cols.stop]).all()
     caps = []

@@ -44,16 +44,18 @@ def timed(name, fn, reps=4):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     t = torch.tensor([min(ts[1:])], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    allt = [torch.zeros(1, device="cuda") for _ in range(world)]
+    dist.all_gather(allt, t)
     if rank == 0:
-        print("%-46s %8.2f ms (max over ranks, best of %d)" % (name, t.item(), reps - 1), flush=True)
+        per = [x.item() for x in allt]
+        print("%-46s %8.2f ms (max over ranks, best of %d)  per rank: %s" % (name, max(per), reps - 1, " ".join("%.1f" % v for v in per)), flush=True)
 
 
 lib = _lib.lib()
 timed("LDE -> local send buffer [G][C_r][L/G]", lambda: check(lib.eng_lde_dev(C.c_void_p(dev.data_ptr()), c_r, log_n, r, 1, plan.log_world,
                                                                                 C.c_void_p(coeffs.data_ptr()), C.c_void_p(send.data_ptr()))))
 timed("LDE with fused peer stores", lambda: check(lib.eng_lde_peer_dev(C.c_void_p(dev.data_ptr()), c_r, log_n, r, 1, plan.log_world,
-                                                                        C.c_void_p(coeffs.data_ptr()), C.c_void_p(send.data_ptr()), ex.shard_out)))
+                                                                        C.c_void_p(coeffs.data_ptr()), C.c_void_p(send.data_ptr()), ex.shard_out, rank)))
 with torch.cuda.stream(stream):
     timed("NCCL all_to_all_single", lambda: dist.all_to_all_single(recv, send, output_split_sizes=plan.recv_splits(), input_split_sizes=plan.send_splits(rank)))
 
