@@ -51,7 +51,9 @@ static void replay_mode(const NttLaunch &l, u64 grid) {
     std::vector<u64> sm(l.smem / 8 + 16);
     const NttPass &p = l.p;
     for (u64 bid = 0; bid < grid; bid++) {
-        for (u64 tile = bid; tile < p.num_tiles; tile += grid) {
+        for (u64 tile_i = bid; tile_i < p.num_tiles; tile_i += grid) {
+            u64 tile = tile_i + p.tile_rot;       // same walk as ntt_pass_kernel
+            if (tile >= p.num_tiles) tile -= p.num_tiles;
             for (u32 t = 0; t < l.threads; t++) ntt_load<MODE>(p, sm.data(), tile, t, l.threads);
             replay_rounds<(MODE >= NTT_INTT_P1)>(p, sm.data(), l.threads);
             for (u32 t = 0; t < l.threads; t++) ntt_store<MODE>(p, sm.data(), tile, t, l.threads);
@@ -117,6 +119,25 @@ int emu_batch_sharded(const u64 *values, u32 C, u32 log_n, u32 rate_bits, u32 ca
     for (u64 j = 0; j < L; j++) merkle_hash_leaf(mp, j);
     for (u32 layer = 0; layer < mp.num_layers; layer++)
         for (u64 gidx = 0; gidx < (L >> (layer + 1)); gidx++) merkle_hash_node(mp, layer, gidx);
+    g_tables.clear();
+    return 0;
+}
+
+// Fused exchange (eng_lde_peer_dev): `rank` transforms its C_r columns and the last pass stores row shard g through
+// shard_out[g] = mats[g] + col0 * L/G, mats[g] being "rank g's" leaf matrix [C_total][L/G]; tiles are walked from shard
+// `rank` on.  Returns 0 on success.
+int emu_lde_peer(const u64 *values, u32 C_r, u32 log_n, u32 rate_bits, u64 grid, u32 log_shards, u32 rank, u32 col0,
+                 u64 *const *mats, u64 *coeffs, u64 *scratch) {
+    NttTableStore ts = make_store();
+    const u64 n = (u64)1 << log_n, L = n << rate_bits;
+    std::vector<NttLaunch> plan;
+    if (!ntt_plan_intt(ts, values, n, scratch, n, coeffs, n, C_r, log_n, plan)) return 1;
+    replay(plan, grid);
+    plan.clear();
+    u64 *so[NTT_MAX_SHARDS];
+    for (u32 g = 0; g < (1u << log_shards); g++) so[g] = mats[g] + (size_t)col0 * (L >> log_shards);
+    if (!ntt_plan_lde(ts, coeffs, n, scratch, C_r, log_n, rate_bits, log_shards, plan, so, rank)) return 2;
+    replay(plan, grid);
     g_tables.clear();
     return 0;
 }

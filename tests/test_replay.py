@@ -122,3 +122,33 @@ def test_row_sharded_lde_layout(emu, oracle, C_, log_n, r, log_g):
     b = oracle.Batch.from_values(vals, r, 0)
     for g in range(G):
         assert (lde[g].T == b.leaves[g * (L // G):(g + 1) * (L // G)]).all()
+
+
+@pytest.mark.parametrize("C_,log_n,r,log_g", [(5, 4, 3, 1), (7, 6, 2, 3), (5, 13, 3, 2), (6, 14, 1, 3), (19, 9, 3, 4)])
+def test_fused_exchange_addressing(emu, oracle, C_, log_n, r, log_g):
+    """CPU replay of eng_lde_peer_dev: every emulated rank transforms its column block and the LAST pass of the LDE stores
+    row shard g through shard_out[g] (here: plain host matrices standing in for the peer mappings), walking the shards
+    from its own rank on.  Afterwards matrix g must hold rows [g L/G, (g+1) L/G) of the oracle's leaves, all columns."""
+    G = 1 << log_g
+    n = 1 << log_n; L = n << r; rows = L // G
+    rng = np.random.default_rng(31 * C_ + log_n)
+    vals = rand_field(rng, (C_, n), noncanonical=True)
+    ref = oracle.Batch.from_values(vals, r, 0)
+    mats = [np.zeros((C_, rows), np.uint64) for _ in range(G)]
+    ptrs = (C.c_void_p * G)(*[m.ctypes.data for m in mats])
+    emu.emu_lde_peer.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                 C.POINTER(C.c_void_p), u64p, u64p]
+    emu.emu_lde_peer.restype = C.c_int
+    base, extra = divmod(C_, G)
+    col0 = 0
+    for rank in range(G):
+        c_r = base + (1 if rank < extra else 0)
+        if c_r == 0:
+            continue
+        local = np.ascontiguousarray(vals[col0:col0 + c_r])
+        coeffs = np.zeros((c_r, n), np.uint64); scratch = np.zeros((c_r, L), np.uint64)
+        assert emu.emu_lde_peer(local, c_r, log_n, r, 3, log_g, rank, col0, ptrs, coeffs, scratch) == 0
+        assert (coeffs == ref.coeffs[col0:col0 + c_r]).all()
+        col0 += c_r
+    for g in range(G):
+        assert (mats[g].T == ref.leaves[g * rows:(g + 1) * rows]).all()
