@@ -45,6 +45,7 @@ _SIGNATURES = {
     "eng_batch_from_values_dev": [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint64, C.c_uint32, C.POINTER(_vp)],
     "eng_batch_from_coeffs_dev": [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint64, C.c_uint32, C.POINTER(_vp)],
     "eng_batch_free": [_vp],
+    "eng_release_cached": [],
     "eng_lde_dev": [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32, _vp, _vp],
     "eng_lde_peer_dev": [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32, _vp, _vp, C.POINTER(_vp), C.c_uint32],
     "eng_lde_peer_host": [C.POINTER(_vp), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32, _vp, _vp, C.POINTER(_vp), C.c_uint32],

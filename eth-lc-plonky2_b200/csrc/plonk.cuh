@@ -30,22 +30,26 @@ struct PlkCircuit {
 };
 
 // ---- the alpha-weighted running sum of constraints for both challenges ----
+// alpha^t comes from a table built on the host (every thread walks the same constraint sequence, so the loads are
+// warp-uniform): one multiply-add per term and challenge instead of two products.
+#define PLK_APOW_MAX 256
 struct PlkAcc {
     u64 sum[PLK_MAX_CHALLENGES];   // sum_t alpha^t term_t
-    u64 apow[PLK_MAX_CHALLENGES];  // alpha^t of the next term
-    u64 alpha[PLK_MAX_CHALLENGES];
+    const u64 *apow;               // [PLK_MAX_CHALLENGES][PLK_APOW_MAX] powers of alpha
+    u32 t;                         // index of the next term
 };
 GL_HD void plk_emit(PlkAcc &a, u64 term) {
 #pragma unroll
-    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) {
-        a.sum[c] = gl_mul_add(a.apow[c], term, a.sum[c]);
-        a.apow[c] = gl_mul(a.apow[c], a.alpha[c]);
-    }
+    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.sum[c] = gl_mul_add(a.apow[c * PLK_APOW_MAX + a.t], term, a.sum[c]);
+    a.t++;
 }
-GL_HD void plk_skip(PlkAcc &a, u32 k) {  // advance the powers over k absent constraints
-    for (u32 i = 0; i < k; i++)
-#pragma unroll
-        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.apow[c] = gl_mul(a.apow[c], a.alpha[c]);
+GL_HD void plk_skip(PlkAcc &a, u32 k) { a.t += k; }  // advance over k absent constraints
+// host: fills the table for the given challenges
+static inline void plk_fill_apow(const u64 *alphas, u32 num_challenges, u64 *tab) {
+    for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) {
+        u64 a = c < num_challenges ? alphas[c] % GL_P : 0, v = 1;
+        for (u32 t = 0; t < PLK_APOW_MAX; t++) { tab[c * PLK_APOW_MAX + t] = v; v = h_gl_mul(v, a); }
+    }
 }
 
 // Accessor of the local wires / constants of one LDE point: column-major arrays with a row offset.
@@ -197,6 +201,7 @@ struct QuotParams {
     const u64 *cs, *wires, *zs;    // LDE of constants||sigmas, wires, Z||partial products: [cols][L], bit-reversed rows
     u64 k_is[80];
     u64 beta[PLK_MAX_CHALLENGES], gamma[PLK_MAX_CHALLENGES], alpha[PLK_MAX_CHALLENGES];
+    const u64 *apow;               // plk_fill_apow(alpha): [PLK_MAX_CHALLENGES][PLK_APOW_MAX]
     u64 pi_hash[4];
     u64 zh[8], zh_inv[8];          // ZeroPolyOnCoset: 7^n w_8^i - 1 and inverses
     u64 n_field;                   // n as a field element
@@ -219,20 +224,21 @@ GL_HD void quot_point(const QuotParams &p, u64 pos) {
     const u32 npp = (C.num_routed + C.quotient_degree_factor - 1) / C.quotient_degree_factor - 1;
     PlkCols cs = {p.cs, L, pos}, sig = {p.cs + (u64)nc * L, L, pos}, w = {p.wires, L, pos}, zs = {p.zs, L, pos}, zn = {p.zs, L, pos_next};
     PlkAcc acc;
-    for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) { acc.sum[c] = 0; acc.apow[c] = 1; acc.alpha[c] = p.alpha[c]; }
+    for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
+    acc.apow = p.apow; acc.t = 0;
     // L_0(x) (Z - 1)
     const u64 l0 = gl_mul(p.zh[i & 7], gl_inverse(gl_mul(p.n_field, gl_sub(x, 1))));
     for (u32 c = 0; c < nch; c++) plk_emit(acc, gl_mul(l0, gl_sub(zs[c], 1)));
-    // partial-product checks, challenge-major
+    // partial-product checks, challenge-major.  beta * k_j * x = (beta x) * k_j: one product per wire and challenge
     for (u32 c = 0; c < nch; c++) {
+        const u64 bx = gl_mul(p.beta[c], x);
         for (u32 t = 0; t <= npp; t++) {
             u64 prev = t == 0 ? zs[c] : zs[nch + c * npp + t - 1];
             u64 next = t == npp ? zn[c] : zs[nch + c * npp + t];
             u64 num = 1, den = 1;
             for (u32 j = t * C.quotient_degree_factor; j < (t + 1) * C.quotient_degree_factor && j < C.num_routed; j++) {
                 u64 wv = w[j];
-                u64 s_id = gl_mul(p.k_is[j], x);
-                num = gl_mul(num, gl_add(gl_mul_add(p.beta[c], s_id, wv), p.gamma[c]));
+                num = gl_mul(num, gl_add(gl_mul_add(bx, p.k_is[j], wv), p.gamma[c]));
                 den = gl_mul(den, gl_add(gl_mul_add(p.beta[c], sig[j], wv), p.gamma[c]));
             }
             plk_emit(acc, gl_sub(gl_mul(prev, num), gl_mul(next, den)));
@@ -266,11 +272,12 @@ GL_HD void pp_row(const PpParams &p, u64 i) {
     const u64 x = gl_mul(p.w_lo[i & ((1ull << p.w_lo_bits) - 1)], p.w_hi[i >> p.w_lo_bits]);
     for (u32 c = 0; c < p.num_challenges; c++) {
         u64 run = 1;
+        const u64 bx = gl_mul(p.beta[c], x);
         for (u32 t = 0; t < nchunks; t++) {
             u64 num = 1, den = 1;
             for (u32 j = t * p.degree; j < (t + 1) * p.degree && j < p.num_routed; j++) {
                 u64 wv = p.wires[(u64)j * n + i];
-                num = gl_mul(num, gl_add(gl_mul_add(p.beta[c], gl_mul(p.k_is[j], x), wv), p.gamma[c]));
+                num = gl_mul(num, gl_add(gl_mul_add(bx, p.k_is[j], wv), p.gamma[c]));
                 den = gl_mul(den, gl_add(gl_mul_add(p.beta[c], p.sigmas[(u64)j * n + i], wv), p.gamma[c]));
             }
             run = gl_mul(run, gl_mul(num, gl_inverse(den)));

@@ -44,6 +44,9 @@ eng_status eng_shutdown(void);
 eng_status eng_last_error(char *buf, size_t len); /* message of the calling thread's last failure */
 eng_status eng_set_stream(void *cuda_stream);     /* run on the caller's cudaStream_t (NULL = engine's own) */
 eng_status eng_synchronize(void);
+/* Released device buffers are kept (by exact size) for the next call of the same shape; this returns them, and the
+ * stream-ordered pool's unused memory, to the driver. */
+eng_status eng_release_cached(void);
 eng_status eng_launch_count(uint64_t *out);       /* kernels launched by the engine since eng_init */
 
 /* Measured integer issue rates of this device, thread-operations per second:

@@ -182,6 +182,9 @@ void emu_quotient_values(const u64 *blob, const u64 *cs_lde, const u64 *wires_ld
     q.k_is[0] = 1;
     for (int j = 1; j < 80; j++) q.k_is[j] = h_gl_mul(q.k_is[j - 1], 7);
     for (u32 i = 0; i < q.C.num_challenges; i++) { q.beta[i] = betas[i]; q.gamma[i] = gammas[i]; q.alpha[i] = alphas[i]; }
+    std::vector<u64> apow_tab((size_t)PLK_MAX_CHALLENGES * PLK_APOW_MAX);
+    plk_fill_apow(q.alpha, q.C.num_challenges, apow_tab.data());
+    q.apow = apow_tab.data();
     for (int i = 0; i < 4; i++) q.pi_hash[i] = pi_hash[i];
     const u64 g_pow_n = h_gl_pow(7, n), w8 = h_gl_root_of_unity(3);
     for (int i = 0; i < 8; i++) { q.zh[i] = gl_canon(gl_sub(h_gl_mul(g_pow_n, h_gl_pow(w8, i)), 1)); q.zh_inv[i] = h_gl_inv(q.zh[i]); }
