@@ -142,6 +142,11 @@ def set_stream(cuda_stream_handle):
     check(lib().eng_set_stream(_vp(cuda_stream_handle or 0)))
 
 
+def release_cached():
+    """eng_release_cached: return cached device buffers and the pool's unused memory to the driver."""
+    check(lib().eng_release_cached())
+
+
 def synchronize():
     check(lib().eng_synchronize())
 
