@@ -65,7 +65,7 @@ struct Ctx {
     std::map<std::pair<u64, u32>, NttTableStore::W2> pow_cache;   // two-level power tables of arbitrary bases
     std::multimap<size_t, void *> free_blocks;      // exact-size cache of released device buffers (dev_alloc / dev_free)
     std::map<void *, size_t> live_blocks;
-    size_t cached_bytes = 0;
+    size_t cached_bytes = 0, cache_cap = (size_t)64 << 30;
     // host-input pipeline: copies run on copy_stream while the previous column chunk transforms on `stream`
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_ev = nullptr, fork_ev = nullptr;
@@ -171,6 +171,7 @@ void dev_free(void *p) {
     if (it == g.live_blocks.end()) { cudaFreeAsync(p, g.stream); return; }
     const size_t bytes = it->second;
     g.live_blocks.erase(it);
+    if (g.cached_bytes + bytes > g.cache_cap) cache_flush();   // many different shapes: do not hoard the device
     g.free_blocks.emplace(bytes, p);
     g.cached_bytes += bytes;
 }
@@ -459,6 +460,7 @@ eng_status eng_init(int32_t device) {
     CU(cudaGetDeviceProperties(&prop, device));
     g.device = device;
     g.sm_count = prop.multiProcessorCount;
+    g.cache_cap = (size_t)(0.6 * (double)prop.totalGlobalMem);
     CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
     for (auto &ev : g.ev) CU(cudaEventCreate(&ev));
