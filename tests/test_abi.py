@@ -55,3 +55,12 @@ def test_no_device_fails_loudly():
     assert ei.value.status == E.ENG_ERR_STATE
     with pytest.raises(E.EngineError):
         E.poseidon([0] * 12)                     # no silent CPU fallback
+
+
+def test_rust_sys_declarations_match_the_header():
+    """integration/plonky2-b200-sys/src/lib.rs is generated from include/plonky2_b200.h (tools/gen_rust_sys.py): the
+    reference-side binding cannot drift from the C ABI."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"])
+    assert r.returncode == 0, "run python tools/gen_rust_sys.py"
