@@ -223,7 +223,13 @@ def main():
     log_n = args.log_n + (world.bit_length() - 1)
     n = 1 << log_n
     plan = E.ShardPlan(cols, log_n, RATE_BITS, CAP_HEIGHT, world) if distributed else None
-    exchange = E.PeerExchange(plan, rank, torch.device("cuda", local_rank)) if distributed and args.exchange == "peer" else None
+    exchange = None
+    if distributed and args.exchange == "peer":
+        try:      # collective: either every rank gets the fused exchange or every rank falls back to the NCCL all-to-all
+            exchange = E.PeerExchange(plan, rank, torch.device("cuda", local_rank))
+        except E.EngineError as ex:
+            if rank == 0:
+                print("bench: %s -- falling back to --exchange nccl" % ex, file=sys.stderr)
     my_cols = plan.columns_of(rank) if distributed else range(cols)
     # synthetic witness, generated on the host, pinned for the e2e path
     host = torch.from_numpy(E.splitmix_columns(len(my_cols), n, first_col=my_cols.start).view(np.int64)).pin_memory()

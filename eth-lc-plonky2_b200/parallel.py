@@ -115,25 +115,55 @@ class PeerExchange:
         self.plan, self.rank, self.group, self.dist = plan, rank, group, dist
         lib = _lib.lib()
         elems = plan.num_polys * plan.rows_per_rank
+        self.local_ptr, self.bases, self._opened = None, [], []
+        self._token = torch.zeros(1, dtype=torch.int32, device=device)
         ptr = C.c_void_p()
         handle = C.create_string_buffer(64)
-        check(lib.eng_peer_buffer_alloc(elems, C.byref(ptr), handle))
-        self.local_ptr = ptr.value
+        # every step is followed by an agreement (all-reduce of a failure count): a rank that cannot allocate or cannot
+        # map a peer must not leave the others waiting inside a collective
+        err = None
+        try:
+            check(lib.eng_peer_buffer_alloc(elems, C.byref(ptr), handle))
+            self.local_ptr = ptr.value
+        except EngineError as e:
+            err = e
+        self._agree(err, "allocating the exchange buffer")
         handles = [None] * plan.world
         dist.all_gather_object(handles, handle.raw, group=group)
-        self.bases, self._opened = [], []
-        for g in range(plan.world):
-            if g == rank:
-                self.bases.append(self.local_ptr)
-            else:
-                q = C.c_void_p()
-                check(lib.eng_peer_buffer_open(handles[g], C.byref(q)))
-                self.bases.append(q.value)
-                self._opened.append(q.value)
+        try:
+            for g in range(plan.world):
+                if g == rank:
+                    self.bases.append(self.local_ptr)
+                else:
+                    q = C.c_void_p()
+                    check(lib.eng_peer_buffer_open(handles[g], C.byref(q)))
+                    self.bases.append(q.value)
+                    self._opened.append(q.value)
+        except EngineError as e:
+            err = e
+        self._agree(err, "mapping the peers' exchange buffers (CUDA IPC / peer access)")
         off = plan.col_offsets[rank] * plan.rows_per_rank * 8     # this rank's first column inside every leaf matrix
         self.shard_out = (C.c_void_p * plan.world)(*[b + off for b in self.bases])
         self.recv = torch.as_tensor(_DevArray(self.local_ptr, elems), device=device)
-        self._token = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def _agree(self, err, what):
+        """Collective: raises on EVERY rank if any rank failed."""
+        self._token.fill_(1 if err is not None else 0)
+        self.dist.all_reduce(self._token, group=self.group)
+        failed = int(self._token.item())
+        self._token.zero_()
+        if failed:
+            self._release_local()
+            raise EngineError(_lib.ENG_ERR_CUDA, "fused exchange unavailable: %d rank(s) failed %s%s" % (failed, what, ": %s" % err if err else ""))
+
+    def _release_local(self):
+        lib = _lib.lib()
+        for q in self._opened:
+            lib.eng_peer_buffer_close(C.c_void_p(q))
+        self._opened = []
+        if self.local_ptr:
+            lib.eng_peer_buffer_free(C.c_void_p(self.local_ptr))
+            self.local_ptr = None
 
     def barrier(self):
         self.dist.all_reduce(self._token, group=self.group)
