@@ -144,6 +144,12 @@ static inline cudaError_t psd_f64_upload_tables() {
 #endif
 
 // ---- primitives ----
+// PF_TRACK_FOLD / PF_TRACK_RENORM: host-only hooks of the CPU replay (tests/emu) recording the range of the values that
+// enter a fold (needs -2^51 <= x < 2^51) and a re-normalisation (accumulated sums, < 2^50).  Nothing in the product.
+#ifndef PF_TRACK_FOLD
+#define PF_TRACK_FOLD(x)
+#define PF_TRACK_RENORM(x)
+#endif
 #ifndef PF_CVT_MAGIC
 #define PF_CVT_MAGIC 0   // 0: I2F.F64.U32 on the conversion unit; 1: 2^52-mantissa trick (one more DADD, two moves)
 #endif
@@ -174,6 +180,8 @@ GL_HD u64 pf_bits(double x) {
 // (al, ah), both in (-2^51, 2^51)  ->  some u64 = (al + 2^51) + 2^32 * (ah + 2^51)  (mod p).
 // With ua = a0 + 2^32 a1, uh = h0 + 2^32 h1 (a1, h1 < 2^20):  value = (a0 - h1) + 2^32 * (a1 + h0 + h1).
 GL_HD u64 pf_fold(double al, double ah) {
+    PF_TRACK_FOLD(al);
+    PF_TRACK_FOLD(ah);
     const u64 ua = pf_bits(al + PF_MAGIC), uh = pf_bits(ah + PF_MAGIC);   // mantissa = x + 2^51
 #ifdef __CUDA_ARCH__
     u32 v0, v1;
@@ -208,6 +216,8 @@ GL_HD u64 pf_fold(double al, double ah) {
 
 // re-normalise a pair without changing lo + 2^32 hi (mod p):  |lo|, |hi| < 2^50  ->  |lo| <= 2^31 + 2^18, |hi| <= 2^31 + 2^19
 GL_HD void pf_renorm(double &lo, double &hi) {
+    PF_TRACK_RENORM(lo);
+    PF_TRACK_RENORM(hi);
     const double I32 = 1.0 / 4294967296.0, N32 = -4294967296.0;
     const double a1 = pf_fma(lo, I32, PF_MAGIC) - PF_MAGIC;   // rint(lo / 2^32)
     const double a0 = pf_fma(a1, N32, lo);

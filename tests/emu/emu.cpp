@@ -5,11 +5,16 @@
 // replays every launch of a plan block by block, thread by thread, phase by phase (each __syncthreads()
 // boundary is a loop boundary).  It checks the index math, table construction and planner on the CPU against
 // the oracle before GPU minutes are spent; the `-m gpu` tests then check the real kernels through the C ABI.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
+// ranges seen by poseidon_f64.cuh's tracking hooks: [0] min and [1] max entering a fold, [2] largest |x| entering a renorm
+static double g_pf_range[3] = {0.0, 0.0, 0.0};
+#define PF_TRACK_FOLD(x) do { double v__ = (x); if (v__ < g_pf_range[0]) g_pf_range[0] = v__; if (v__ > g_pf_range[1]) g_pf_range[1] = v__; } while (0)
+#define PF_TRACK_RENORM(x) do { double a__ = std::fabs(x); if (a__ > g_pf_range[2]) g_pf_range[2] = a__; } while (0)
 #include "../../eth-lc-plonky2_b200/csrc/merkle.cuh"
 #include "../../eth-lc-plonky2_b200/csrc/ntt.cuh"
 #include "../../eth-lc-plonky2_b200/csrc/ntt_plan.h"
@@ -230,4 +235,9 @@ extern "C" void emu_poseidon_permute_f64(const u64 *in, u64 *out, size_t count) 
         poseidon_permute_f64(s);
         for (int k = 0; k < 12; k++) out[12 * i + k] = gl_canon(s[k]);
     }
+}
+
+// ranges seen at the folds / re-normalisations since the last reset
+extern "C" void emu_poseidon_f64_ranges(double *out, int reset) {
+    for (int i = 0; i < 3; i++) { out[i] = g_pf_range[i]; if (reset) g_pf_range[i] = 0.0; }
 }

@@ -27,6 +27,7 @@ def emu():
     L = C.CDLL(so)
     L.emu_poseidon_permute.argtypes = [u64p, u64p, C.c_size_t]
     L.emu_poseidon_permute_f64.argtypes = [u64p, u64p, C.c_size_t]
+    L.emu_poseidon_f64_ranges.argtypes = [C.POINTER(C.c_double), C.c_int]
     L.emu_batch_from_values.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, u64p, u64p, u64p, u64p]
     L.emu_batch_from_values.restype = C.c_int
     L.emu_plan.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u64p, C.c_int]
@@ -152,3 +153,22 @@ def test_fused_exchange_addressing(emu, oracle, C_, log_n, r, log_g):
         col0 += c_r
     for g in range(G):
         assert (mats[g].T == ref.leaves[g * rows:(g + 1) * rows]).all()
+
+
+def test_poseidon_fp64_magnitudes_stay_exact(emu):
+    """The FP64 formulation is exact as long as every value entering a fold lies in [-2^51, 2^51) (the fold reads the
+    mantissa of x + 1.5 * 2^52) and the accumulated sums stay far below 2^53.  The CPU replay records those ranges over
+    random and adversarial states (all-ones, p - 1, alternating extremes)."""
+    rng = np.random.default_rng(11)
+    st = rand_field(rng, (20000, 12), noncanonical=True)
+    st[0] = 2**64 - 1; st[1] = P - 1; st[2] = np.array([0, 2**64 - 1] * 6, np.uint64); st[3] = np.array([2**64 - 1, 0] * 6, np.uint64)
+    st[4] = 2**63; st[5] = 2**32 - 1; st[6] = 2**64 - 2**32; st[7] = 0
+    out = np.zeros_like(st)
+    r = (C.c_double * 3)()
+    emu.emu_poseidon_f64_ranges(r, 1)
+    emu.emu_poseidon_permute_f64(st, out, st.shape[0])
+    emu.emu_poseidon_f64_ranges(r, 1)
+    fold_min, fold_max, renorm_max = r[0], r[1], r[2]
+    assert -2.0**51 <= fold_min and fold_max < 2.0**51, (fold_min, fold_max)
+    assert fold_max < 2.0**49                      # accumulated sums (observed ~2^48); -2^51 only as the explicit bias
+    assert 2.0**40 < renorm_max < 2.0**50, renorm_max
