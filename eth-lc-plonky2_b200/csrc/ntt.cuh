@@ -261,7 +261,13 @@ GL_HD gl96 l3_from(u64 x) { gl96 r; r.w0 = (u32)x; r.w1 = (u32)(x >> 32); r.w2 =
 #ifndef __CUDA_ARCH__
 typedef __int128 l3_i128;
 GL_HD l3_i128 l3_val(gl96 a) { return (l3_i128)a.w0 + ((l3_i128)a.w1 << 32) + ((l3_i128)(int32_t)a.w2) * ((l3_i128)1 << 64); }
+// L3_TRACK: host-only hook of the CPU replay recording the largest lazy magnitude (the 96-bit two's-complement form and
+// l3_shl's 128-bit intermediate need |v| < 2^80)
+#ifndef L3_TRACK
+#define L3_TRACK(v)
+#endif
 GL_HD gl96 l3_make(l3_i128 v) {
+    L3_TRACK(v);
     gl96 r; r.w0 = (u32)v; r.w1 = (u32)(v >> 32); r.w2 = (u32)(v >> 64);
     return r;   // callers stay far below 2^95; the GPU code wraps identically
 }

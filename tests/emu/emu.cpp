@@ -15,6 +15,8 @@
 static double g_pf_range[3] = {0.0, 0.0, 0.0};
 #define PF_TRACK_FOLD(x) do { double v__ = (x); if (v__ < g_pf_range[0]) g_pf_range[0] = v__; if (v__ > g_pf_range[1]) g_pf_range[1] = v__; } while (0)
 #define PF_TRACK_RENORM(x) do { double a__ = std::fabs(x); if (a__ > g_pf_range[2]) g_pf_range[2] = a__; } while (0)
+static double g_l3_maxabs = 0.0;   // largest lazy 96-bit magnitude built by ntt.cuh's l3_* helpers (L3_TRACK hook)
+#define L3_TRACK(v) do { double a__ = std::fabs((double)(v)); if (a__ > g_l3_maxabs) g_l3_maxabs = a__; } while (0)
 #include "../../eth-lc-plonky2_b200/csrc/merkle.cuh"
 #include "../../eth-lc-plonky2_b200/csrc/ntt.cuh"
 #include "../../eth-lc-plonky2_b200/csrc/ntt_plan.h"
@@ -240,4 +242,10 @@ extern "C" void emu_poseidon_permute_f64(const u64 *in, u64 *out, size_t count) 
 // ranges seen at the folds / re-normalisations since the last reset
 extern "C" void emu_poseidon_f64_ranges(double *out, int reset) {
     for (int i = 0; i < 3; i++) { out[i] = g_pf_range[i]; if (reset) g_pf_range[i] = 0.0; }
+}
+
+extern "C" double emu_l3_maxabs(int reset) {
+    double v = g_l3_maxabs;
+    if (reset) g_l3_maxabs = 0.0;
+    return v;
 }

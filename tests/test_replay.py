@@ -172,3 +172,24 @@ def test_poseidon_fp64_magnitudes_stay_exact(emu):
     assert -2.0**51 <= fold_min and fold_max < 2.0**51, (fold_min, fold_max)
     assert fold_max < 2.0**49                      # accumulated sums (observed ~2^48); -2^51 only as the explicit bias
     assert 2.0**40 < renorm_max < 2.0**50, renorm_max
+
+
+def test_ntt_lazy_values_stay_in_range(emu, oracle):
+    """The radix-16 DFT rounds add and subtract LAZILY on 96-bit two's-complement values (no wrap correction) and shift them
+    by up to 31 bits into a 128-bit intermediate: that is exact while |v| < 2^80.  The CPU replay records the largest lazy
+    magnitude over a commit of all-ones columns (every butterfly input at its maximum) and a random one."""
+    emu.emu_l3_maxabs.argtypes = [C.c_int]
+    emu.emu_l3_maxabs.restype = C.c_double
+    C_, log_n, r = 3, 13, 3
+    n = 1 << log_n; L = n << r
+    worst = np.full((C_, n), 2**64 - 1, np.uint64)
+    worst[1] = P - 1
+    worst[2] = rand_field(np.random.default_rng(2), (n,), noncanonical=True)
+    coeffs = np.zeros((C_, n), np.uint64); lde = np.zeros((C_, L), np.uint64)
+    dig = np.zeros((2 * (L - 1), 4), np.uint64); cap = np.zeros((1, 4), np.uint64)
+    emu.emu_l3_maxabs(1)
+    assert emu.emu_batch_from_values(worst, C_, log_n, r, 0, 1, 3, coeffs, lde, dig, cap) == 0
+    m = emu.emu_l3_maxabs(1)
+    assert 2.0**64 < m < 2.0**72, m            # 16 inputs below 2^64 summed: < 2^68; shift results stay below 2^66
+    b = oracle.Batch.from_values(worst, r, 0)
+    assert (b.coeffs == coeffs).all() and (b.leaves == lde.T).all()
