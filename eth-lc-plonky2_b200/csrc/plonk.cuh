@@ -153,6 +153,120 @@ GL_HD void plk_poseidon_gate(const W &w, u64 filter, PlkAcc &acc) {
     }
 }
 
+// The same constraints with the linear layers of the permutation in exact FP64 (poseidon_f64.cuh): the S-box inputs the
+// gate constrains are the same values in the naive and in the "fast" partial rounds, so the constraint stream is
+// identical term for term.  OFF by default in round 1 (validated by the CPU replay only; flip PLK_POSEIDON_F64 after a
+// GPU parity run -- DESIGN.md section 9).
+#ifndef PLK_POSEIDON_F64
+#define PLK_POSEIDON_F64 0
+#endif
+template <class W>
+GL_HD void plk_poseidon_gate_f64(const W &w, u64 filter, PlkAcc &acc) {
+    const u64 swap = w[24];
+    plk_emit(acc, gl_mul(filter, gl_mul(swap, gl_sub(swap, 1))));
+    u64 st[12];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u64 lhs = w[i], rhs = w[i + 4], d = w[25 + i];
+        plk_emit(acc, gl_mul(filter, gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), d)));
+        st[i] = gl_add(lhs, d);
+        st[i + 4] = gl_sub(rhs, d);
+    }
+#pragma unroll
+    for (int i = 8; i < 12; i++) st[i] = w[i];
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i] = gl_add_c(st[i], PSD_RC(i));     // state + RC_0
+    double al[12], ah[12];
+    // first half: S-box (on the wire values from round 1 on), MDS with RC_{r+1} in the chain heads, fold
+    PSD_UNROLL1
+    for (int r = 0; r < 4; r++) {
+        double xl[12], xh[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            u64 v = st[i];
+            if (r != 0) {
+                const u64 in = w[29 + 12 * (r - 1) + i];
+                plk_emit(acc, gl_mul(filter, gl_sub(v, in)));
+                v = in;
+            }
+            pf_pow7(v, xl[i], xh[i]);
+        }
+        pf_circ12(xl, PF_T(sc1), PF_T(full_init_s)[r][0], al);
+        pf_circ12(xh, PF_T(sc1), PF_T(full_init_s)[r][1], ah);
+        al[0] = pf_fma(xl[0], 8.0, al[0]);
+        ah[0] = pf_fma(xh[0], 8.0, ah[0]);
+#pragma unroll
+        for (int i = 0; i < 12; i++) st[i] = pf_fold(al[i], ah[i]);
+    }
+    // partial rounds, two per step (pf_partial_rounds with the two S-box inputs constrained and replaced by the wires)
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        al[j] = pf_cvt((u32)st[j]);
+        ah[j] = pf_cvt((u32)(st[j] >> 32));
+    }
+    al[0] -= 2251799813685248.0;
+    ah[0] -= 2251799813685248.0;
+    PSD_UNROLL1
+    for (int p = 0; p < 11; p++) {
+        const u64 a = pf_fold(al[0], ah[0]);
+        const u64 in0 = w[65 + 2 * p];
+        plk_emit(acc, gl_mul(filter, gl_sub(a, in0)));
+#pragma unroll
+        for (int j = 1; j < 12; j++) pf_renorm(al[j], ah[j]);
+        pf_pow7(in0, al[0], ah[0]);
+        double t0l = PF_T(pair_t0)[p][0], t0h = PF_T(pair_t0)[p][1];
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            t0l = pf_fma(al[j], PF_T(circ)[j], t0l);
+            t0h = pf_fma(ah[j], PF_T(circ)[j], t0h);
+        }
+        t0l = pf_fma(al[0], 8.0, t0l);
+        t0h = pf_fma(ah[0], 8.0, t0h);
+        const u64 b = pf_fold(t0l, t0h);
+        const u64 in1 = w[65 + 2 * p + 1];
+        plk_emit(acc, gl_mul(filter, gl_sub(b, in1)));
+        double nl[12], nh[12];
+        pf_circ12(al, PF_T(sc2), PF_T(pair_k_s)[p][0], nl);
+        pf_circ12(ah, PF_T(sc2), PF_T(pair_k_s)[p][1], nh);
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+            nl[r] = pf_fma(al[0], PF_T(col8)[r], nl[r]);
+            nh[r] = pf_fma(ah[0], PF_T(col8)[r], nh[r]);
+        }
+        nl[0] = pf_fma(t0l, 8.0, nl[0]);
+        nh[0] = pf_fma(t0h, 8.0, nh[0]);
+        double bl, bh;
+        pf_pow7(in1, bl, bh);
+        const double dl = bl - t0l, dh = bh - t0h;   // lane 0 is REPLACED by in1^7: the difference is against the computed b
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+            al[r] = pf_fma(PF_T(m_col0)[r], dl, nl[r]);
+            ah[r] = pf_fma(PF_T(m_col0)[r], dh, nh[r]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i] = pf_fold(al[i], ah[i]);          // state + RC_26
+    // second half
+    PSD_UNROLL1
+    for (int r = 0; r < 4; r++) {
+        double xl[12], xh[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            const u64 in = w[87 + 12 * r + i];
+            plk_emit(acc, gl_mul(filter, gl_sub(st[i], in)));
+            pf_pow7(in, xl[i], xh[i]);
+        }
+        pf_circ12(xl, PF_T(sc1), PF_T(full_init_s)[4 + r][0], al);
+        pf_circ12(xh, PF_T(sc1), PF_T(full_init_s)[4 + r][1], ah);
+        al[0] = pf_fma(xl[0], 8.0, al[0]);
+        ah[0] = pf_fma(xh[0], 8.0, ah[0]);
+#pragma unroll
+        for (int i = 0; i < 12; i++) st[i] = pf_fold(al[i], ah[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) plk_emit(acc, gl_mul(filter, gl_sub(st[i], w[12 + i])));
+}
+
 // compute_filter(row, group, s, many_selectors)
 GL_HD u64 plk_filter(u32 row, u32 gs, u32 ge, u64 s, bool many) {
     u64 f = 1;
@@ -186,7 +300,11 @@ GL_HD void plk_gate_constraints(const PlkCircuit &C, const W &w, const K &consts
                 plk_emit(acc, gl_mul(filter, gl_sub(o, computed)));
             }
         } else if (gt.kind == PLK_POSEIDON) {
+#if PLK_POSEIDON_F64
+            plk_poseidon_gate_f64(w, filter, acc);
+#else
             plk_poseidon_gate(w, filter, acc);
+#endif
         }
 #pragma unroll
         for (int c = 0; c < PLK_MAX_CHALLENGES; c++) total[c] = gl_add(total[c], acc.sum[c]);

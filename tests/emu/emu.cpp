@@ -180,6 +180,8 @@ static void emu_fill_circuit(const u64 *b, PlkCircuit &C) {
 void emu_quotient_values(const u64 *blob, const u64 *cs_lde, const u64 *wires_lde, const u64 *zs_lde, const u64 *pi_hash,
                          const u64 *betas, const u64 *gammas, const u64 *alphas, u64 *out) {
     NttTableStore ts = make_store();
+    static bool pf_built = false;   // the FP64 PoseidonGate evaluator (PLK_POSEIDON_F64) reads the host tables
+    if (!pf_built) { psd_f64_build_tables(h_pf); pf_built = true; }
     QuotParams q;
     memset(&q, 0, sizeof(q));
     emu_fill_circuit(blob, q.C);
