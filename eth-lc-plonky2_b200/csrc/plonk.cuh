@@ -160,45 +160,13 @@ GL_HD void plk_poseidon_gate(const W &w, u64 filter, PlkAcc &acc) {
 #ifndef PLK_POSEIDON_F64
 #define PLK_POSEIDON_F64 0
 #endif
+#ifndef PLK_F64_LANES
+#define PLK_F64_LANES 3   // S-box lanes per rolled iteration (code size: the kernel must stay inside the instruction cache)
+#endif
+// the 22 partial rounds of the gate, two per step: pf_partial_rounds with both S-box inputs constrained and replaced
 template <class W>
-GL_HD void plk_poseidon_gate_f64(const W &w, u64 filter, PlkAcc &acc) {
-    const u64 swap = w[24];
-    plk_emit(acc, gl_mul(filter, gl_mul(swap, gl_sub(swap, 1))));
-    u64 st[12];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        u64 lhs = w[i], rhs = w[i + 4], d = w[25 + i];
-        plk_emit(acc, gl_mul(filter, gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), d)));
-        st[i] = gl_add(lhs, d);
-        st[i + 4] = gl_sub(rhs, d);
-    }
-#pragma unroll
-    for (int i = 8; i < 12; i++) st[i] = w[i];
-#pragma unroll
-    for (int i = 0; i < 12; i++) st[i] = gl_add_c(st[i], PSD_RC(i));     // state + RC_0
+GL_HD void plk_poseidon_gate_f64_partial(const W &w, u64 filter, PlkAcc &acc, u64 (&st)[12]) {
     double al[12], ah[12];
-    // first half: S-box (on the wire values from round 1 on), MDS with RC_{r+1} in the chain heads, fold
-    PSD_UNROLL1
-    for (int r = 0; r < 4; r++) {
-        double xl[12], xh[12];
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            u64 v = st[i];
-            if (r != 0) {
-                const u64 in = w[29 + 12 * (r - 1) + i];
-                plk_emit(acc, gl_mul(filter, gl_sub(v, in)));
-                v = in;
-            }
-            pf_pow7(v, xl[i], xh[i]);
-        }
-        pf_circ12(xl, PF_T(sc1), PF_T(full_init_s)[r][0], al);
-        pf_circ12(xh, PF_T(sc1), PF_T(full_init_s)[r][1], ah);
-        al[0] = pf_fma(xl[0], 8.0, al[0]);
-        ah[0] = pf_fma(xh[0], 8.0, ah[0]);
-#pragma unroll
-        for (int i = 0; i < 12; i++) st[i] = pf_fold(al[i], ah[i]);
-    }
-    // partial rounds, two per step (pf_partial_rounds with the two S-box inputs constrained and replaced by the wires)
 #pragma unroll
     for (int j = 0; j < 12; j++) {
         al[j] = pf_cvt((u32)st[j]);
@@ -246,25 +214,74 @@ GL_HD void plk_poseidon_gate_f64(const W &w, u64 filter, PlkAcc &acc) {
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) st[i] = pf_fold(al[i], ah[i]);          // state + RC_26
-    // second half
+}
+template <class W>
+GL_HD void plk_poseidon_gate_f64(const W &w, u64 filter, PlkAcc &acc) {
+    const u64 swap = w[24];
+    plk_emit(acc, gl_mul(filter, gl_mul(swap, gl_sub(swap, 1))));
+    u64 st[12];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u64 lhs = w[i], rhs = w[i + 4], d = w[25 + i];
+        plk_emit(acc, gl_mul(filter, gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), d)));
+        st[i] = gl_add(lhs, d);
+        st[i + 4] = gl_sub(rhs, d);
+    }
+#pragma unroll
+    for (int i = 8; i < 12; i++) st[i] = w[i];
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i] = gl_add_c(st[i], PSD_RC(i));     // state + RC_0
+    // ONE rolled copy of the full round (layers 0..7; the partial rounds sit between 3 and 4): S-box on the wire values
+    // (from round 1 on), MDS with the next round's constants in the chain heads, fold.  The lanes run PLK_F64_LANES per
+    // iteration with the state rotated through the registers, as in poseidon_f64.cuh.
     PSD_UNROLL1
-    for (int r = 0; r < 4; r++) {
+    for (int L = 0; L < 8; L++) {
+        if (L == 4) plk_poseidon_gate_f64_partial(w, filter, acc, st);
+        const u32 wire0 = L < 4 ? 29 + 12 * (L - 1) : 87 + 12 * (L - 4);   // sbox-in wires of this round (none for L = 0)
         double xl[12], xh[12];
 #pragma unroll
-        for (int i = 0; i < 12; i++) {
-            const u64 in = w[87 + 12 * r + i];
-            plk_emit(acc, gl_mul(filter, gl_sub(st[i], in)));
-            pf_pow7(in, xl[i], xh[i]);
+        for (int k = 0; k < 12; k++) xl[k] = xh[k] = 0.0;
+        PSD_UNROLL1
+        for (int it = 0; it < 12 / PLK_F64_LANES; it++) {
+            double tl[PLK_F64_LANES], th[PLK_F64_LANES];
+#pragma unroll
+            for (int k = 0; k < PLK_F64_LANES; k++) {
+                u64 v = st[k];
+                if (L != 0) {
+                    const u64 in = w[wire0 + PLK_F64_LANES * it + k];
+                    plk_emit(acc, gl_mul(filter, gl_sub(v, in)));
+                    v = in;
+                }
+                pf_pow7(v, tl[k], th[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 12 - PLK_F64_LANES; k++) {
+                st[k] = st[k + PLK_F64_LANES];
+                xl[k] = xl[k + PLK_F64_LANES];
+                xh[k] = xh[k + PLK_F64_LANES];
+            }
+#pragma unroll
+            for (int k = 0; k < PLK_F64_LANES; k++) {
+                xl[12 - PLK_F64_LANES + k] = tl[k];
+                xh[12 - PLK_F64_LANES + k] = th[k];
+            }
         }
-        pf_circ12(xl, PF_T(sc1), PF_T(full_init_s)[4 + r][0], al);
-        pf_circ12(xh, PF_T(sc1), PF_T(full_init_s)[4 + r][1], ah);
+        double al[12], ah[12];
+        pf_circ12(xl, PF_T(sc1), PF_T(full_init_s)[L][0], al);
+        pf_circ12(xh, PF_T(sc1), PF_T(full_init_s)[L][1], ah);
         al[0] = pf_fma(xl[0], 8.0, al[0]);
         ah[0] = pf_fma(xh[0], 8.0, ah[0]);
 #pragma unroll
         for (int i = 0; i < 12; i++) st[i] = pf_fold(al[i], ah[i]);
     }
+    PSD_UNROLL1
+    for (int i = 0; i < 12; i++) {
+        plk_emit(acc, gl_mul(filter, gl_sub(st[0], w[12 + i])));
+        u64 t = st[0];          // rotate by one so that the rolled loop always reads st[0]
 #pragma unroll
-    for (int i = 0; i < 12; i++) plk_emit(acc, gl_mul(filter, gl_sub(st[i], w[12 + i])));
+        for (int k = 0; k < 11; k++) st[k] = st[k + 1];
+        st[11] = t;
+    }
 }
 
 // compute_filter(row, group, s, many_selectors)
