@@ -155,10 +155,10 @@ GL_HD void plk_poseidon_gate(const W &w, u64 filter, PlkAcc &acc) {
 
 // The same constraints with the linear layers of the permutation in exact FP64 (poseidon_f64.cuh): the S-box inputs the
 // gate constrains are the same values in the naive and in the "fast" partial rounds, so the constraint stream is
-// identical term for term.  OFF by default in round 1 (validated by the CPU replay only; flip PLK_POSEIDON_F64 after a
-// GPU parity run -- DESIGN.md section 9).
+// identical term for term.  Default since the GPU parity run of round 1 (tests/test_gpu_plonk.py: 13 proofs bit-exact and
+// verifying; quotient 35.1 -> 33.8 ms at 2^20 rows); -DPLK_POSEIDON_F64=0 keeps the integer evaluator for A/B.
 #ifndef PLK_POSEIDON_F64
-#define PLK_POSEIDON_F64 0
+#define PLK_POSEIDON_F64 1
 #endif
 #ifndef PLK_F64_LANES
 #define PLK_F64_LANES 3   // S-box lanes per rolled iteration (code size: the kernel must stay inside the instruction cache)

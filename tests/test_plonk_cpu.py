@@ -55,26 +55,26 @@ def test_partial_products_replay(emu, oracle, synth, db):
 
 
 @pytest.fixture(scope="module")
-def emu_f64_gate():
-    """The replay harness built with -DPLK_POSEIDON_F64=1: the PoseidonGate evaluator whose permutation runs its linear
-    layers in exact FP64 (off by default in round 1 -- DESIGN.md section 9 -- but kept bit-exact here)."""
+def emu_int_gate():
+    """The replay harness built with -DPLK_POSEIDON_F64=0: the PoseidonGate evaluator on the integer pipes ("fast" partial
+    rounds), kept as the A/B baseline of the default FP64 evaluator."""
     import os
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     src = os.path.join(here, "emu", "emu.cpp")
-    so = os.path.join(here, "emu", "libemu_f64gate.so")
+    so = os.path.join(here, "emu", "libemu_intgate.so")
     csrc = os.path.join(here, "..", "eth-lc-plonky2_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DPLK_POSEIDON_F64=1", "-o", so, src])
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DPLK_POSEIDON_F64=0", "-o", so, src])
     return C.CDLL(so)
 
 
-@pytest.mark.parametrize("variant", ["default", "f64_gate"])
+@pytest.mark.parametrize("variant", ["default", "int_gate"])
 @pytest.mark.parametrize("db", [3, 5])
-def test_quotient_point_replay(emu, emu_f64_gate, oracle, synth, db, variant):
-    if variant == "f64_gate":
-        emu = emu_f64_gate
+def test_quotient_point_replay(emu, emu_int_gate, oracle, synth, db, variant):
+    if variant == "int_gate":
+        emu = emu_int_gate
     emu.emu_quotient_values.argtypes = [u64p] * 9
     s = synth[db]
     circ = oracle.Circuit(s["blob"])
