@@ -80,12 +80,22 @@ def _worker(rank, world, port, shape, out_dir):
     except E.EngineError:
         pass
     open(os.path.join(out_dir, "rank%d" % rank), "w").write("ok" if ok else "FAIL")
+    dist.barrier()                      # nobody tears its sockets down while a peer is still draining the last collective
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world,shape", [(2, (9, 5, 3, 4)), (2, (5, 4, 1, 1)), (4, (11, 6, 3, 4)), (2, (135, 4, 3, 4))])
 def test_sharded_commit_matches_single_process(tmp_path, world, shape):
-    mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path)), nprocs=world, join=True)
+    for attempt in range(2):
+        try:
+            mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path)), nprocs=world, join=True)
+            break
+        except mp.ProcessExitedException:
+            # a worker killed by a signal is gloo / rendezvous infrastructure (seen once in ~40 runs, on a cold page cache),
+            # not a wrong result: results are judged from the files the workers write.  One retry, then fail.
+            if attempt == 1 or any((tmp_path / ("rank%d" % r)).exists() and open(tmp_path / ("rank%d" % r)).read() != "ok"
+                                   for r in range(world)):
+                raise
     for r in range(world):
         assert open(tmp_path / ("rank%d" % r)).read() == "ok"
 
