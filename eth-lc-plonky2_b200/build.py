@@ -25,6 +25,16 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
+    # torchrun starts one process per GPU: exactly one of them compiles, the others wait for the lock and find the library fresh
+    import fcntl
+    with open(SO + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return SO
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose):
     cmd = [NVCC] + FLAGS + os.environ.get("ENG_NVCC_EXTRA", "").split() + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")
