@@ -17,6 +17,7 @@ cpu_baseline   the C++/OpenMP oracle (a restatement of plonky2's CPU algorithm -
                built here) timed on the host cores on a bounded sample of the same workload.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -170,6 +171,21 @@ def proof_section(E, log_n, reps=4):
             "reference_published": "~300 s for the real 2^22-row circuit on 32 vCPU (README.md:71); not comparable 1:1"}
 
 
+def dist_roofline(stages, cols, n, world):
+    """N > 1: rank 0's leaf hashing (the dominant kernel, identical work on every rank) against the integer-pipe roofline."""
+    try:
+        leaf_ms = stages.get("build Merkle tree (leaves)", 0.0)
+        if leaf_ms <= 0:
+            return None
+        perms = ((n << RATE_BITS) // world) * ((cols + 7) // 8)      # per rank and launch
+        rate = perms * IMAD_PER_PERM / (leaf_ms * 1e-3)
+        return {"kernel": "merkle_leaves_kernel on rank 0 (%d permutations per launch)" % perms, "bound": "int32-imad",
+                "achieved": rate / 1e12, "peak": NOMINAL_IMAD_PER_S / 1e12, "unit": "TIMAD32/s", "frac": rate / NOMINAL_IMAD_PER_S,
+                "traffic": None, "kernel_ms": leaf_ms}
+    except Exception:   # noqa: BLE001
+        return None
+
+
 def exchange_close(exchange):
     if exchange is not None:
         exchange.close()
@@ -246,7 +262,14 @@ def main():
     def step_device():
         if distributed:
             b = E.ShardedPolynomialBatch.from_values(dev, plan, rank, exchange=exchange)
-            return {k: 0.0 for k in stage_keys}
+            ms = {k: 0.0 for k in stage_keys}
+            try:     # this rank's hashing times (CUDA events inside eng_merkle_new_dev); the transform is timed as a whole
+                t = (ctypes.c_float * 6)()
+                if E._lib.lib().eng_batch_stage_ms(b.merkle_tree_local._o._h, t) == 0:
+                    ms["build Merkle tree (leaves)"], ms["build Merkle tree (digest levels)"] = float(t[3]), float(t[4])
+            except Exception:   # noqa: BLE001
+                pass
+            return ms
         b = E.PolynomialBatch.from_values(dev, RATE_BITS, False, CAP_HEIGHT)
         ms = b.stage_ms()
         b.close()
@@ -320,6 +343,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "GB/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": 8 * cols * n, "d2h_bytes_per_step": (32 << CAP_HEIGHT) * world},
                 "gpu_launches": launches, "clocks": clocks, "cap0": "%016x" % int(cap_e2e[0][0]),
+                "stage_ms": stages, "roofline": dist_roofline(stages, cols, n, world),
                 "exchange": ("fused: the LDE's last pass stores %.2f GB per rank into the peers' leaf matrices (NVLink P2P, CUDA IPC); NCCL carries two "
                              "barriers and the cap all_gather" if exchange is not None else
                              "all_to_all_single of %.2f GB per rank (NCCL), cap all_gather") % (8 * len(my_cols) * (n << RATE_BITS) * (world - 1) / world / 1e9),
