@@ -27,6 +27,12 @@ class BatchInfo(C.Structure):
                 ("num_leaves", C.c_uint64), ("num_digests", C.c_uint64)]
 
 
+class CircuitInfo(C.Structure):
+    _fields_ = [(k, C.c_uint32) for k in ("degree_bits", "num_wires", "num_routed_wires", "num_constants", "num_selectors", "num_challenges",
+                                          "quotient_degree_factor", "num_partial_products", "rate_bits", "cap_height", "num_gates",
+                                          "num_gate_constraints")]
+
+
 _u64p = C.POINTER(C.c_uint64)
 _vp = C.c_void_p
 _SIGNATURES = {
@@ -36,6 +42,7 @@ _SIGNATURES = {
     "eng_set_stream": [_vp],
     "eng_synchronize": [],
     "eng_launch_count": [_u64p],
+    "eng_set_option": [C.c_char_p, C.c_int64],
     "eng_measure_int_peak": [C.POINTER(C.c_double)],
     "eng_poseidon_permute": [_vp, _vp, C.c_size_t],
     "eng_hash_n": [_vp, C.c_size_t, C.c_size_t, C.c_int32, _vp],
@@ -75,6 +82,16 @@ _SIGNATURES = {
     "eng_blob_free": [_u64p],
     "eng_circuit_new": [_vp, _vp, C.POINTER(_vp), C.POINTER(_vp)],
     "eng_circuit_free": [_vp],
+    "eng_circuit_info": [_vp, C.POINTER(CircuitInfo)],
+    "eng_circuit_describe": [_vp, _vp, C.c_uint32, _vp, C.POINTER(_u64p), C.POINTER(C.c_size_t)],
+    "eng_circuit_save": [_vp, _vp, C.c_char_p],
+    "eng_circuit_load": [C.c_char_p, C.POINTER(_vp), C.POINTER(_u64p), C.POINTER(C.c_size_t)],
+    "eng_circuit_constants_sigmas": [_vp, C.POINTER(_vp)],
+    "eng_verify": [_vp, _vp, _vp, _vp, C.c_size_t],
+    "eng_proof_to_bytes": [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)],
+    "eng_proof_from_bytes": [_vp, _vp, C.c_size_t, C.POINTER(_u64p), C.POINTER(C.c_size_t), C.POINTER(_u64p), C.POINTER(C.c_size_t)],
+    "eng_bytes_free": [C.POINTER(C.c_uint8)],
+    "eng_synth_circuit_v2": [C.c_uint32, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint32), C.POINTER(_u64p), C.POINTER(C.c_size_t)],
     "eng_partial_products": [_vp, C.POINTER(_vp), _vp, _vp, _vp],
     "eng_quotient": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)],
     "eng_prove": [_vp, C.POINTER(_vp), _vp, C.POINTER(_u64p), C.POINTER(C.c_size_t), C.POINTER(C.c_float)],
@@ -140,6 +157,11 @@ def lib():
 
 def set_stream(cuda_stream_handle):
     check(lib().eng_set_stream(_vp(cuda_stream_handle or 0)))
+
+
+def set_option(name, value):
+    """eng_set_option: A/B switches of the engine (see include/plonky2_b200.h)."""
+    check(load().eng_set_option(name.encode(), int(value)))
 
 
 def release_cached():

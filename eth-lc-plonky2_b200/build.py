@@ -23,9 +23,9 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return SO
-    # torchrun starts one process per GPU: exactly one of them compiles, the others wait for the lock and find the library fresh
+    # torchrun starts one process per GPU: exactly one of them compiles, the others wait for the lock and find the library
+    # fresh.  The freshness check happens UNDER the lock, and nvcc writes to a temporary path that is renamed onto SO, so
+    # a rank arriving mid-build can neither skip the lock on a fresh-looking mtime nor dlopen a half-written file.
     import fcntl
     with open(SO + ".lock", "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
@@ -35,8 +35,13 @@ def build(force=False, verbose=False):
 
 
 def _build_locked(verbose):
-    cmd = [NVCC] + FLAGS + os.environ.get("ENG_NVCC_EXTRA", "").split() + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = "%s.tmp.%d" % (SO, os.getpid())
+    cmd = [NVCC] + FLAGS + os.environ.get("ENG_NVCC_EXTRA", "").split() + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode == 0:
+        os.replace(tmp, SO)          # atomic swap
+    elif os.path.exists(tmp):
+        os.remove(tmp)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout)

@@ -5,6 +5,7 @@
 // plonky2::hash::merkle_tree::MerkleTree::{new, get, prove} (dep plonky2 0.1.4, /root/reference/Cargo.lock:2347-2350),
 // reached from /root/reference/eth-lc-plonky2/src/main.rs:227 (build) and :230 (prove).
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -20,8 +21,10 @@
 #include "ntt.cuh"
 #include "ntt_plan.h"
 #include "prover.cuh"
+#include "gate_lib.h"
 #include "plonk.cuh"
 #include <map>
+#include <sys/random.h>
 
 #define SALT_SIZE 4u
 
@@ -73,6 +76,10 @@ struct Ctx {
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     size_t stage_elems = 0;
     int stage_next = 0;
+    bool table_upload_failed = false;        // a twiddle / power table could not be placed on the device (reported by tables_ok)
+    // eng_set_option
+    int opt_native_poseidon = 1;             // quotient: PoseidonGate through the native FP64 evaluator (0: its bytecode)
+    int opt_lde_group_mb = 48;               // LDE: megabytes of one (column, coset) group kept between the two passes (L2 residency)
 };
 Ctx g;
 
@@ -92,14 +99,60 @@ struct eng_batch {
 
 namespace {
 
-__global__ void salt_kernel(u64 *dst, u64 count, u64 seed) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    u64 z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    z ^= z >> 31;
-    dst[i] = gl_canon(z);
+// Blinding salts (PolynomialBatch::from_coeffs with blinding: SALT_SIZE random elements per leaf; plonky2 draws them from
+// OsRng through F::rand_vec).  Here: the ChaCha20 key stream under a 256-bit key -- taken from the OS RNG (getrandom) for
+// every batch unless the caller asks for the reproducible test stream -- block counter = thread index.  One 64-byte block
+// gives 4 salts from its first four 64-bit words; a word >= p (probability 2^-32) is replaced by the next spare word of the
+// block (rejection sampling, as rand's gen_range does), so the salts are uniform in [0, p) and one opened leaf says
+// nothing about the others.
+struct SaltKey { u32 k[8]; };
+__device__ __forceinline__ u32 salt_rotl(u32 x, int n) { return (x << n) | (x >> (32 - n)); }
+#define SALT_QR(a, b, c, d) a += b; d = salt_rotl(d ^ a, 16); c += d; b = salt_rotl(b ^ c, 12); a += b; d = salt_rotl(d ^ a, 8); c += d; b = salt_rotl(b ^ c, 7);
+__global__ void salt_kernel(u64 *dst, u64 count, SaltKey key) {
+    const u64 blk = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk * 4 >= count) return;
+    u32 st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.k[0], key.k[1], key.k[2], key.k[3],
+                  key.k[4], key.k[5], key.k[6], key.k[7], (u32)blk, (u32)(blk >> 32), 0u, 0u};
+    u32 x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = st[i];
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) {
+        SALT_QR(x[0], x[4], x[8], x[12]) SALT_QR(x[1], x[5], x[9], x[13]) SALT_QR(x[2], x[6], x[10], x[14]) SALT_QR(x[3], x[7], x[11], x[15])
+        SALT_QR(x[0], x[5], x[10], x[15]) SALT_QR(x[1], x[6], x[11], x[12]) SALT_QR(x[2], x[7], x[8], x[13]) SALT_QR(x[3], x[4], x[9], x[14])
+    }
+    u64 w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = (u64)(x[2 * i] + st[2 * i]) | ((u64)(x[2 * i + 1] + st[2 * i + 1]) << 32);
+    int spare = 4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u64 v = w[i];
+        while (v >= GL_P && spare < 8) v = w[spare++];
+        if (blk * 4 + i < count) dst[blk * 4 + i] = gl_canon(v);   // all spares used (2^-160): canonicalise
+    }
+}
+// key of one batch: 32 bytes of OS randomness, or -- ONLY for reproducible tests -- the ChaCha-style expansion of a seed
+eng_status salt_key(uint64_t seed, SaltKey &key) {
+    if (seed == 0) {
+        size_t got = 0;
+        while (got < sizeof(key.k)) {
+            ssize_t r = getrandom((char *)key.k + got, sizeof(key.k) - got, 0);
+            if (r <= 0) return fail(ENG_ERR_STATE, "getrandom failed: blinding needs the OS random number generator");
+            got += (size_t)r;
+        }
+        return ENG_OK;
+    }
+    u64 z = seed;
+    for (int i = 0; i < 4; i++) {
+        z += 0x9E3779B97F4A7C15ULL;
+        u64 v = z;
+        v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        v = (v ^ (v >> 27)) * 0x94D049BB133111EBULL;
+        v ^= v >> 31;
+        key.k[2 * i] = (u32)v; key.k[2 * i + 1] = (u32)(v >> 32);
+    }
+    return ENG_OK;
 }
 __global__ void permute_kernel(const u64 *in, u64 *out, size_t count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,6 +229,25 @@ void dev_free(void *p) {
     g.cached_bytes += bytes;
 }
 
+// Scope guard for temporary device buffers: every early return releases them (error paths leaked).
+struct DevBuf {
+    u64 *p = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    eng_status alloc(size_t elems) { release(); return dev_alloc(&p, elems); }
+    void release() { if (p) { dev_free(p); p = nullptr; } }
+    u64 *take() { u64 *q = p; p = nullptr; return q; }
+};
+
+// A table upload that failed is not cached (NttTableStore drops it) and poisons nothing: the call that needed it fails here.
+eng_status tables_ok() {
+    if (!g.table_upload_failed) return ENG_OK;
+    g.table_upload_failed = false;
+    return fail(ENG_ERR_OOM, "device allocation of a twiddle table failed");
+}
+
 template <int MODE>
 eng_status launch_mode(const NttLaunch &l) {
     static bool attr_set = false;
@@ -196,6 +268,7 @@ eng_status launch_mode(const NttLaunch &l) {
     return ENG_OK;
 }
 eng_status launch_plan(const std::vector<NttLaunch> &plan) {
+    ST(tables_ok());
     for (const NttLaunch &l : plan) {
         switch (l.mode) {
             case NTT_LDE_FIRST: ST(launch_mode<NTT_LDE_FIRST>(l)); break;
@@ -420,7 +493,9 @@ eng_status make_batch(const uint64_t *const *cols_host, const u64 *src_dev, bool
     }
     if (blinding) {
         u64 count = (u64)SALT_SIZE * L;
-        salt_kernel<<<(unsigned)((count + 255) / 256), 256, 0, g.stream>>>(b->lde + (size_t)C * L, count, seed);
+        SaltKey key;
+        STB(salt_key(seed, key));
+        salt_kernel<<<(unsigned)((count / 4 + 255) / 256), 256, 0, g.stream>>>(b->lde + (size_t)C * L, count, key);
         g.launches++;
         CUB(cudaGetLastError());
     }
@@ -474,8 +549,10 @@ eng_status eng_init(int32_t device) {
     CU(poseidon_upload_constants());
     g.tables.upload = [](const std::vector<u64> &t) -> const u64 * {
         void *d = nullptr;
-        if (cudaMalloc(&d, t.size() * sizeof(u64)) != cudaSuccess) return nullptr;
-        cudaMemcpy(d, t.data(), t.size() * sizeof(u64), cudaMemcpyHostToDevice);
+        if (cudaMalloc(&d, t.size() * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); g.table_upload_failed = true; return nullptr; }
+        if (cudaMemcpy(d, t.data(), t.size() * sizeof(u64), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(d); g.table_upload_failed = true; return nullptr;
+        }
         g.table_allocs.push_back(d);
         return (const u64 *)d;
     };
@@ -542,6 +619,14 @@ eng_status eng_synchronize(void) {
     return ENG_OK;
 }
 
+eng_status eng_set_option(const char *name, int64_t value) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!name) return fail(ENG_ERR_INVALID, "NULL option name");
+    if (!strcmp(name, "quot_native_poseidon")) { g.opt_native_poseidon = value != 0; return ENG_OK; }
+    if (!strcmp(name, "lde_group_mb")) { g.opt_lde_group_mb = value < 0 ? 0 : (int)value; return ENG_OK; }
+    return fail(ENG_ERR_INVALID, "unknown option '%s'", name);
+}
+
 eng_status eng_launch_count(uint64_t *out) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!out) return ENG_ERR_INVALID;
@@ -585,16 +670,14 @@ eng_status eng_poseidon_permute(const uint64_t *states_host, uint64_t *out_host,
     ST(check_ready());
     if (count == 0) return ENG_OK;
     if (!states_host || !out_host) return fail(ENG_ERR_INVALID, "NULL buffer");
-    u64 *d_in, *d_out;
-    ST(dev_alloc(&d_in, count * 12));
-    ST(dev_alloc(&d_out, count * 12));
-    CU(cudaMemcpyAsync(d_in, states_host, count * 96, cudaMemcpyHostToDevice, g.stream));
-    permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, g.stream>>>(d_in, d_out, count);
+    DevBuf d_in, d_out;
+    ST(d_in.alloc(count * 12));
+    ST(d_out.alloc(count * 12));
+    CU(cudaMemcpyAsync(d_in.p, states_host, count * 96, cudaMemcpyHostToDevice, g.stream));
+    permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, g.stream>>>(d_in.p, d_out.p, count);
     g.launches++;
     CU(cudaGetLastError());
-    eng_status s = d2h(out_host, d_out, count * 96);
-    dev_free(d_in); dev_free(d_out);
-    return s;
+    return d2h(out_host, d_out.p, count * 96);
 }
 
 eng_status eng_hash_n(const uint64_t *in_host, size_t len, size_t count, int32_t or_noop, uint64_t *out_host) {
@@ -603,9 +686,10 @@ eng_status eng_hash_n(const uint64_t *in_host, size_t len, size_t count, int32_t
     if (count == 0) return ENG_OK;
     if ((!in_host && len) || !out_host) return fail(ENG_ERR_INVALID, "NULL buffer");
     if (len >= (1ull << 32)) return fail(ENG_ERR_INVALID, "input too long");
-    u64 *d_in, *d_dig;
-    ST(dev_alloc(&d_in, count * (len ? len : 1)));
-    ST(dev_alloc(&d_dig, count * 4));
+    DevBuf in_buf, dig_buf;
+    ST(in_buf.alloc(count * (len ? len : 1)));
+    ST(dig_buf.alloc(count * 4));
+    u64 *d_in = in_buf.p, *d_dig = dig_buf.p;
     if (len) CU(cudaMemcpyAsync(d_in, in_host, count * len * 8, cudaMemcpyHostToDevice, g.stream));
     // a zero-layer "tree" whose cap is the leaf digests: one sponge per row
     MerkleParams mp;
@@ -618,7 +702,6 @@ eng_status eng_hash_n(const uint64_t *in_host, size_t len, size_t count, int32_t
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) s = fail(ENG_ERR_CUDA, "merkle_leaves_kernel: %s", cudaGetErrorString(e));
     if (s == ENG_OK) s = d2h(out_host, d_dig, count * 32);
-    dev_free(d_in); dev_free(d_dig);
     return s;
 }
 
@@ -627,16 +710,14 @@ eng_status eng_two_to_one(const uint64_t *pairs_host, size_t count, uint64_t *ou
     ST(check_ready());
     if (count == 0) return ENG_OK;
     if (!pairs_host || !out_host) return fail(ENG_ERR_INVALID, "NULL buffer");
-    u64 *d_in, *d_out;
-    ST(dev_alloc(&d_in, count * 8));
-    ST(dev_alloc(&d_out, count * 4));
-    CU(cudaMemcpyAsync(d_in, pairs_host, count * 64, cudaMemcpyHostToDevice, g.stream));
-    two_to_one_kernel<<<(unsigned)((count + 127) / 128), 128, 0, g.stream>>>(d_in, d_out, count);
+    DevBuf d_in, d_out;
+    ST(d_in.alloc(count * 8));
+    ST(d_out.alloc(count * 4));
+    CU(cudaMemcpyAsync(d_in.p, pairs_host, count * 64, cudaMemcpyHostToDevice, g.stream));
+    two_to_one_kernel<<<(unsigned)((count + 127) / 128), 128, 0, g.stream>>>(d_in.p, d_out.p, count);
     g.launches++;
     CU(cudaGetLastError());
-    eng_status s = d2h(out_host, d_out, count * 32);
-    dev_free(d_in); dev_free(d_out);
-    return s;
+    return d2h(out_host, d_out.p, count * 32);
 }
 
 eng_status eng_batch_from_values(const uint64_t *const *cols_host, uint32_t num_polys, uint32_t log_n, uint32_t rate_bits,
@@ -849,11 +930,12 @@ eng_status eng_merkle_new(const uint64_t *leaves_host, uint64_t num_leaves, uint
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     ST(merkle_check(num_leaves, leaf_len, cap_height, out));
     if (!leaves_host && leaf_len) return fail(ENG_ERR_INVALID, "leaves_host is NULL");
-    u64 *buf = nullptr;
-    ST(dev_alloc(&buf, (size_t)num_leaves * (leaf_len ? leaf_len : 1)));
+    DevBuf buf;
+    ST(buf.alloc((size_t)num_leaves * (leaf_len ? leaf_len : 1)));
     CU(cudaEventRecord(g.ev[0], g.stream));
-    if (leaf_len) CU(cudaMemcpyAsync(buf, leaves_host, (size_t)num_leaves * leaf_len * 8, cudaMemcpyHostToDevice, g.stream));
-    return merkle_common(buf, true, leaf_len, 1, num_leaves, leaf_len, cap_height, out, buf);
+    if (leaf_len) CU(cudaMemcpyAsync(buf.p, leaves_host, (size_t)num_leaves * leaf_len * 8, cudaMemcpyHostToDevice, g.stream));
+    const u64 *data = buf.p;
+    return merkle_common(data, true, leaf_len, 1, num_leaves, leaf_len, cap_height, out, buf.take());
 }
 
 eng_status eng_merkle_new_dev(const uint64_t *data_dev, uint64_t row_stride, uint64_t col_stride, uint64_t num_leaves,
@@ -898,15 +980,13 @@ eng_status eng_batch_coeffs(const eng_batch *b, uint32_t poly, uint64_t *out_hos
 
 static eng_status gather_rows(const eng_batch *b, uint64_t first, uint64_t count, uint32_t width, uint64_t *out_host) {
     if (count == 0 || width == 0) return ENG_OK;
-    u64 *tmp;
-    ST(dev_alloc(&tmp, (size_t)count * width));
+    DevBuf tmp;
+    ST(tmp.alloc((size_t)count * width));
     u64 total = count * width;
-    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g.stream>>>(b->leaf_data, b->row_stride, b->col_stride, width, first, count, tmp);
+    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g.stream>>>(b->leaf_data, b->row_stride, b->col_stride, width, first, count, tmp.p);
     g.launches++;
-    cudaError_t e = cudaGetLastError();
-    eng_status s = e == cudaSuccess ? d2h(out_host, tmp, (size_t)total * 8) : fail(ENG_ERR_CUDA, "gather_rows_kernel: %s", cudaGetErrorString(e));
-    dev_free(tmp);
-    return s;
+    CU(cudaGetLastError());
+    return d2h(out_host, tmp.p, (size_t)total * 8);
 }
 
 eng_status eng_batch_leaves(const eng_batch *b, uint64_t first, uint64_t count, uint64_t *out_host) {
@@ -968,3 +1048,5 @@ eng_status eng_batch_stage_ms(const eng_batch *b, float out[6]) {
 
 #include "engine_prover.inc"
 #include "engine_plonk.inc"
+#include "engine_verify.inc"
+#include "engine_synth.inc"

@@ -35,7 +35,9 @@ struct NttTableStore {
         if (inverse) w = h_gl_inv(w);
         t[0] = 1;
         for (size_t i = 1; i < half; i++) t[i] = h_gl_mul(t[i - 1], w);
-        return tw_local_cache[key] = upload(t);
+        const u64 *d = upload(t);
+        if (!d) return nullptr;            // a failed upload is not cached (the owner reports it)
+        return tw_local_cache[key] = d;
     }
     // two-level powers of w_n (inverse: w_n^-1)
     W2 w2(int log_n, bool inverse) {
@@ -53,6 +55,7 @@ struct NttTableStore {
         hi[0] = 1;
         for (size_t i = 1; i < nhi; i++) hi[i] = h_gl_mul(hi[i - 1], wh);
         W2 r = {upload(lo), upload(hi), lo_bits};
+        if (!r.lo || !r.hi) return r;
         return w2_cache[key] = r;
     }
     // s_e = 7 * w_L^e, e < 2^rate_bits:  a[e][j] = s_e^(j * st), j < P;  b[e][r] = s_e^r, r < st;  st = n / P
@@ -72,6 +75,7 @@ struct NttTableStore {
             for (size_t r = 1; r < st; r++) b[e * st + r] = h_gl_mul(b[e * st + r - 1], s);
         }
         Shift r = {upload(a), upload(b)};
+        if (!r.a || !r.b) return r;
         return shift_cache[key] = r;
     }
 };

@@ -2,53 +2,54 @@
 //
 // Replaces plonky2::plonk::prover::{wires_permutation_partial_products_and_zs, compute_quotient_polys},
 // plonky2::plonk::vanishing_poly::{eval_vanishing_poly_base_batch, evaluate_gate_constraints_base_batch},
-// plonk_common::{check_partial_products, ZeroPolyOnCoset} and Gate::eval_unfiltered_base_batch of the five core
-// gates restated in SURVEY.md A.8 (dep plonky2 0.1.4, /root/reference/Cargo.lock:2347-2350; reached from
-// /root/reference/eth-lc-plonky2/src/main.rs:230).  The other gates of the real eth-lc circuit (plonky2_crypto's u32 /
-// comparison gates, the recursion gates) need their source and plug in as further cases of
-// quot_gate_constraints.
+// plonk_common::{check_partial_products, ZeroPolyOnCoset} and every Gate::eval_unfiltered_base_batch (dep plonky2 0.1.4,
+// /root/reference/Cargo.lock:2347-2350; reached from /root/reference/eth-lc-plonky2/src/main.rs:230).  Gates are DATA:
+// each gate of the circuit arrives as a bytecode program (gate_vm.h) -- recorded on the Rust side from the gate's own
+// eval_unfiltered_circuit, or built by gate_lib.h for the gates restated there -- so the recursion gates
+// (/root/reference/eth-lc-plonky2/src/targets.rs:468-470), plonky2_crypto's u32 gates (merkle_tree_gadget.rs:37) and
+// BaseSumGate (utils.rs:102-103) need no per-gate port.  PoseidonGate additionally has a native evaluator (the FP64
+// permutation of poseidon_f64.cuh), checked bit for bit against its bytecode.
 //
-// B200 design: one thread per LDE point, reading the column-major LDE of the three committed batches (coalesced);
-// every gate's constraints are folded on the fly into sum_t alpha^t * filter * c_t for both challenges (no
-// per-point constraint vectors, no re-packing into "batches of 32" as the CPU code does); the row-sequential Z
-// accumulation of plonky2 becomes a three-phase multiplicative scan.
+// B200 design: one thread per point of the quotient domain, reading the column-major LDE of the three committed batches
+// (coalesced).  The work is split into kernels that each fit the instruction cache and their register budget:
+//   quot_perm_kernel      L_0(x)(Z - 1) and the partial-product checks            -> acc[c][pos]  =
+//   quot_poseidon_kernel  PoseidonGate through the FP64 permutation                -> acc[c][pos] +=
+//   quot_gates_kernel     every other gate through the bytecode interpreter        -> acc[c][pos] +=
+//   quot_finish_kernel    * 1 / Z_H(x), scatter into natural order for the coset iNTT
+// A gate streams sum_t alpha^(base + t) c_t and is multiplied by its selector filter ONCE.  L_0(x) comes from a per-circuit
+// table built with a batched (Montgomery) inversion; the row-sequential Z accumulation of plonky2 is a three-phase
+// multiplicative scan, with one batched inversion per row for the chunk denominators.
 #pragma once
 #include "gl64.cuh"
+#include "gate_vm.h"
 #include "poseidon.cuh"
 #include "prover.cuh"
 
-enum { PLK_NOOP = 0, PLK_CONSTANT = 1, PLK_PUBLIC_INPUT = 2, PLK_ARITHMETIC = 3, PLK_POSEIDON = 4 };
-#define PLK_MAX_GATES 16
 #define PLK_MAX_CHALLENGES 2
+#define PLK_MAX_ROUTED 80
+#define PLK_MAX_CHUNKS 40          // num_routed / quotient_degree_factor, quotient_degree_factor >= 2
+#define PLK_MAX_ZH 16              // 2^quotient_degree_bits <= 2^rate_bits <= 16
 #define PLK_UNUSED_SELECTOR 0xFFFFFFFFull
-
-struct PlkGate { u32 kind, selector_index, group_start, group_end; };
-struct PlkCircuit {
-    u32 degree_bits, num_wires, num_routed, num_gate_constants, num_selectors, num_challenges, quotient_degree_factor;
-    u32 num_gates;
-    PlkGate gates[PLK_MAX_GATES];
-};
 
 // ---- the alpha-weighted running sum of constraints for both challenges ----
 // alpha^t comes from a table built on the host (every thread walks the same constraint sequence, so the loads are
-// warp-uniform): one multiply-add per term and challenge instead of two products.
-#define PLK_APOW_MAX 256
+// warp-uniform): one multiply-add per term and challenge.
 struct PlkAcc {
     u64 sum[PLK_MAX_CHALLENGES];   // sum_t alpha^t term_t
-    const u64 *apow;               // [PLK_MAX_CHALLENGES][PLK_APOW_MAX] powers of alpha
+    const u64 *apow;               // [PLK_MAX_CHALLENGES][stride] powers of alpha
+    u32 stride;
     u32 t;                         // index of the next term
 };
 GL_HD void plk_emit(PlkAcc &a, u64 term) {
 #pragma unroll
-    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.sum[c] = gl_mul_add(a.apow[c * PLK_APOW_MAX + a.t], term, a.sum[c]);
+    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.sum[c] = gl_mul_add(a.apow[c * a.stride + a.t], term, a.sum[c]);
     a.t++;
 }
-GL_HD void plk_skip(PlkAcc &a, u32 k) { a.t += k; }  // advance over k absent constraints
 // host: fills the table for the given challenges
-static inline void plk_fill_apow(const u64 *alphas, u32 num_challenges, u64 *tab) {
+static inline void plk_fill_apow(const u64 *alphas, u32 num_challenges, u32 stride, u64 *tab) {
     for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) {
         u64 a = c < num_challenges ? alphas[c] % GL_P : 0, v = 1;
-        for (u32 t = 0; t < PLK_APOW_MAX; t++) { tab[c * PLK_APOW_MAX + t] = v; v = h_gl_mul(v, a); }
+        for (u32 t = 0; t < stride; t++) { tab[c * stride + t] = v; v = h_gl_mul(v, a); }
     }
 }
 
@@ -60,112 +61,16 @@ struct PlkCols {
     GL_HD u64 operator[](u32 j) const { return base[(u64)j * stride + row]; }
 };
 
-// filter * constraints of one gate, streamed into `acc` starting at alpha^(first gate term)
-template <class W>
-GL_HD void plk_poseidon_gate(const W &w, u64 filter, PlkAcc &acc) {
-    const u64 swap = w[24];
-    plk_emit(acc, gl_mul(filter, gl_mul(swap, gl_sub(swap, 1))));
-    u64 st[12];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        u64 lhs = w[i], rhs = w[i + 4], d = w[25 + i];
-        plk_emit(acc, gl_mul(filter, gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), d)));
-        st[i] = gl_add(lhs, d);
-        st[i + 4] = gl_sub(rhs, d);
-    }
-#pragma unroll
-    for (int i = 8; i < 12; i++) st[i] = w[i];
-    PSD_UNROLL1
-    for (int r = 0; r < 4; r++) {
-        PSD_UNROLL1
-        for (int it = 0; it < 12 / PSD_SBOX_LANES; it++) {
-#pragma unroll
-            for (int k = 0; k < PSD_SBOX_LANES; k++) {
-                int i = PSD_SBOX_LANES * it + k;
-                u64 v = gl_add_c(st[k], PSD_RC(12 * r + i));
-                if (r != 0) {
-                    u64 in = w[29 + 12 * (r - 1) + i];
-                    plk_emit(acc, gl_mul(filter, gl_sub(v, in)));
-                    v = in;
-                }
-                st[k] = gl_pow7(v);
-            }
-            poseidon_rot(st);
-        }
-        poseidon_mds(st);
-    }
-#pragma unroll
-    for (int i = 0; i < 12; i++) st[i] = gl_add_c(st[i], PSD_FIRST(i));
-    {
-        u64 o[11];
-#pragma unroll
-        for (int i = 0; i < 11; i++) o[i] = 0;
-        PSD_UNROLL1
-        for (int i = 0; i < 11; i++) {
-            acc160 a = {0, 0, 0};
-#pragma unroll
-            for (int j = 0; j < 11; j++) acc160_mac(a, PSD_INIT(11 * i + j), st[j + 1]);
-            u64 v = acc160_reduce(a);
-#pragma unroll
-            for (int k = 0; k < 10; k++) o[k] = o[k + 1];
-            o[10] = v;
-        }
-#pragma unroll
-        for (int i = 0; i < 11; i++) st[i + 1] = o[i];
-    }
-    PSD_UNROLL1
-    for (int r = 0; r < 22; r++) {
-        u64 in = w[65 + r];
-        plk_emit(acc, gl_mul(filter, gl_sub(st[0], in)));
-        u64 s0 = gl_add_c(gl_pow7(in), PSD_K(r));
-        acc160 a = {0, 0, 0};
-        acc160_mac(a, s0, 25);
-#pragma unroll
-        for (int i = 0; i < 11; i++) acc160_mac(a, PSD_ROW(11 * r + i), st[i + 1]);
-#pragma unroll
-        for (int i = 0; i < 11; i++) st[i + 1] = gl_mul_add(PSD_COL(11 * r + i), s0, st[i + 1]);
-        st[0] = acc160_reduce(a);
-    }
-    PSD_UNROLL1
-    for (int r = 0; r < 4; r++) {
-        PSD_UNROLL1
-        for (int it = 0; it < 12 / PSD_SBOX_LANES; it++) {
-#pragma unroll
-            for (int k = 0; k < PSD_SBOX_LANES; k++) {
-                int i = PSD_SBOX_LANES * it + k;
-                u64 v = gl_add_c(st[k], PSD_RC(12 * (26 + r) + i));
-                u64 in = w[87 + 12 * r + i];
-                plk_emit(acc, gl_mul(filter, gl_sub(v, in)));
-                st[k] = gl_pow7(in);
-            }
-            poseidon_rot(st);
-        }
-        poseidon_mds(st);
-    }
-    PSD_UNROLL1
-    for (int i = 0; i < 12; i++) {
-        plk_emit(acc, gl_mul(filter, gl_sub(st[0], w[12 + i])));
-        // rotate by one so that the rolled loop always reads st[0]
-        u64 t = st[0];
-#pragma unroll
-        for (int k = 0; k < 11; k++) st[k] = st[k + 1];
-        st[11] = t;
-    }
-}
-
-// The same constraints with the linear layers of the permutation in exact FP64 (poseidon_f64.cuh): the S-box inputs the
-// gate constrains are the same values in the naive and in the "fast" partial rounds, so the constraint stream is
-// identical term for term.  Default since the GPU parity run of round 1 (tests/test_gpu_plonk.py: 13 proofs bit-exact and
-// verifying; quotient 35.1 -> 33.8 ms at 2^20 rows); -DPLK_POSEIDON_F64=0 keeps the integer evaluator for A/B.
-#ifndef PLK_POSEIDON_F64
-#define PLK_POSEIDON_F64 1
-#endif
+// ---- native PoseidonGate evaluator: the constraints of [DEP plonky2:gates/poseidon.rs::eval_unfiltered_base_batch] with
+// the linear layers of the permutation in exact FP64 (poseidon_f64.cuh).  The S-box inputs the gate constrains are the
+// same values in the naive and in the "fast" partial rounds, so the constraint stream equals the bytecode's term for term
+// (tests/test_gates_cpu.py, tests/test_gpu_plonk.py::test_native_poseidon_gate_equals_bytecode).
 #ifndef PLK_F64_LANES
 #define PLK_F64_LANES 3   // S-box lanes per rolled iteration (code size: the kernel must stay inside the instruction cache)
 #endif
 // the 22 partial rounds of the gate, two per step: pf_partial_rounds with both S-box inputs constrained and replaced
 template <class W>
-GL_HD void plk_poseidon_gate_f64_partial(const W &w, u64 filter, PlkAcc &acc, u64 (&st)[12]) {
+GL_HD void plk_poseidon_gate_f64_partial(const W &w, PlkAcc &acc, u64 (&st)[12]) {
     double al[12], ah[12];
 #pragma unroll
     for (int j = 0; j < 12; j++) {
@@ -178,7 +83,7 @@ GL_HD void plk_poseidon_gate_f64_partial(const W &w, u64 filter, PlkAcc &acc, u6
     for (int p = 0; p < 11; p++) {
         const u64 a = pf_fold(al[0], ah[0]);
         const u64 in0 = w[65 + 2 * p];
-        plk_emit(acc, gl_mul(filter, gl_sub(a, in0)));
+        plk_emit(acc, gl_sub(a, in0));
 #pragma unroll
         for (int j = 1; j < 12; j++) pf_renorm(al[j], ah[j]);
         pf_pow7(in0, al[0], ah[0]);
@@ -192,7 +97,7 @@ GL_HD void plk_poseidon_gate_f64_partial(const W &w, u64 filter, PlkAcc &acc, u6
         t0h = pf_fma(ah[0], 8.0, t0h);
         const u64 b = pf_fold(t0l, t0h);
         const u64 in1 = w[65 + 2 * p + 1];
-        plk_emit(acc, gl_mul(filter, gl_sub(b, in1)));
+        plk_emit(acc, gl_sub(b, in1));
         double nl[12], nh[12];
         pf_circ12(al, PF_T(sc2), PF_T(pair_k_s)[p][0], nl);
         pf_circ12(ah, PF_T(sc2), PF_T(pair_k_s)[p][1], nh);
@@ -216,14 +121,14 @@ GL_HD void plk_poseidon_gate_f64_partial(const W &w, u64 filter, PlkAcc &acc, u6
     for (int i = 0; i < 12; i++) st[i] = pf_fold(al[i], ah[i]);          // state + RC_26
 }
 template <class W>
-GL_HD void plk_poseidon_gate_f64(const W &w, u64 filter, PlkAcc &acc) {
+GL_HD void plk_poseidon_gate_f64(const W &w, PlkAcc &acc) {
     const u64 swap = w[24];
-    plk_emit(acc, gl_mul(filter, gl_mul(swap, gl_sub(swap, 1))));
+    plk_emit(acc, gl_mul(swap, gl_sub(swap, 1)));
     u64 st[12];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         u64 lhs = w[i], rhs = w[i + 4], d = w[25 + i];
-        plk_emit(acc, gl_mul(filter, gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), d)));
+        plk_emit(acc, gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), d));
         st[i] = gl_add(lhs, d);
         st[i + 4] = gl_sub(rhs, d);
     }
@@ -236,7 +141,7 @@ GL_HD void plk_poseidon_gate_f64(const W &w, u64 filter, PlkAcc &acc) {
     // iteration with the state rotated through the registers, as in poseidon_f64.cuh.
     PSD_UNROLL1
     for (int L = 0; L < 8; L++) {
-        if (L == 4) plk_poseidon_gate_f64_partial(w, filter, acc, st);
+        if (L == 4) plk_poseidon_gate_f64_partial(w, acc, st);
         const u32 wire0 = L < 4 ? 29 + 12 * (L - 1) : 87 + 12 * (L - 4);   // sbox-in wires of this round (none for L = 0)
         double xl[12], xh[12];
 #pragma unroll
@@ -249,7 +154,7 @@ GL_HD void plk_poseidon_gate_f64(const W &w, u64 filter, PlkAcc &acc) {
                 u64 v = st[k];
                 if (L != 0) {
                     const u64 in = w[wire0 + PLK_F64_LANES * it + k];
-                    plk_emit(acc, gl_mul(filter, gl_sub(v, in)));
+                    plk_emit(acc, gl_sub(v, in));
                     v = in;
                 }
                 pf_pow7(v, tl[k], th[k]);
@@ -276,13 +181,20 @@ GL_HD void plk_poseidon_gate_f64(const W &w, u64 filter, PlkAcc &acc) {
     }
     PSD_UNROLL1
     for (int i = 0; i < 12; i++) {
-        plk_emit(acc, gl_mul(filter, gl_sub(st[0], w[12 + i])));
+        plk_emit(acc, gl_sub(st[0], w[12 + i]));
         u64 t = st[0];          // rotate by one so that the rolled loop always reads st[0]
 #pragma unroll
         for (int k = 0; k < 11; k++) st[k] = st[k + 1];
         st[11] = t;
     }
 }
+
+
+struct PlkGateDev {            // one gate of the circuit as the kernels see it
+    u32 prog_off, prog_len;    // words into QuotParams::prog
+    u32 selector_index, group_start, group_end, row;   // row = index of the gate = the selector value that enables it
+    u32 num_constraints, native;                       // native != 0: evaluated by quot_poseidon_kernel, skipped by the interpreter
+};
 
 // compute_filter(row, group, s, many_selectors)
 GL_HD u64 plk_filter(u32 row, u32 gs, u32 ge, u64 s, bool many) {
@@ -293,76 +205,61 @@ GL_HD u64 plk_filter(u32 row, u32 gs, u32 ge, u64 s, bool many) {
     return f;
 }
 
-// All gate constraints of one point.  plonky2 adds the gates' filtered constraints per constraint index and then takes
-// powers of alpha; by linearity each gate streams filter * c_t * alpha^(base + t) from the same starting power.
-template <class W, class K>
-GL_HD void plk_gate_constraints(const PlkCircuit &C, const W &w, const K &consts, const u64 *pi_hash, const PlkAcc &start, u64 *out) {
-    u64 total[PLK_MAX_CHALLENGES] = {0, 0};
-    for (u32 g = 0; g < C.num_gates; g++) {
-        const PlkGate &gt = C.gates[g];
-        if (gt.kind == PLK_NOOP) continue;
-        u64 filter = plk_filter(g, gt.group_start, gt.group_end, consts[gt.selector_index], C.num_selectors > 1);
-        PlkAcc acc = start;
-#pragma unroll
-        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
-        if (gt.kind == PLK_CONSTANT) {
-            for (u32 i = 0; i < 2; i++) plk_emit(acc, gl_mul(filter, gl_sub(consts[C.num_selectors + i], w[i])));
-        } else if (gt.kind == PLK_PUBLIC_INPUT) {
-            for (u32 i = 0; i < 4; i++) plk_emit(acc, gl_mul(filter, gl_sub(w[i], pi_hash[i])));
-        } else if (gt.kind == PLK_ARITHMETIC) {
-            const u64 c0 = consts[C.num_selectors], c1 = consts[C.num_selectors + 1];
-            for (u32 i = 0; i < 20; i++) {
-                u64 m0 = w[4 * i], m1 = w[4 * i + 1], ad = w[4 * i + 2], o = w[4 * i + 3];
-                u64 computed = gl_add(gl_mul(gl_mul(m0, m1), c0), gl_mul(ad, c1));
-                plk_emit(acc, gl_mul(filter, gl_sub(o, computed)));
-            }
-        } else if (gt.kind == PLK_POSEIDON) {
-#if PLK_POSEIDON_F64
-            plk_poseidon_gate_f64(w, filter, acc);
-#else
-            plk_poseidon_gate(w, filter, acc);
-#endif
-        }
-#pragma unroll
-        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) total[c] = gl_add(total[c], acc.sum[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) out[c] = total[c];
-}
-
 struct QuotParams {
-    PlkCircuit C;
-    u32 log_l;                     // degree_bits + 3
-    const u64 *cs, *wires, *zs;    // LDE of constants||sigmas, wires, Z||partial products: [cols][L], bit-reversed rows
-    u64 k_is[80];
-    u64 beta[PLK_MAX_CHALLENGES], gamma[PLK_MAX_CHALLENGES], alpha[PLK_MAX_CHALLENGES];
-    const u64 *apow;               // plk_fill_apow(alpha): [PLK_MAX_CHALLENGES][PLK_APOW_MAX]
-    u64 pi_hash[4];
-    u64 zh[8], zh_inv[8];          // ZeroPolyOnCoset: 7^n w_8^i - 1 and inverses
-    u64 n_field;                   // n as a field element
-    const u64 *w_lo, *w_hi;        // two-level powers of w_L
+    u32 log_n, log_lq;             // rows; quotient domain = 2^log_lq = n * 2^quotient_degree_bits points (<= LDE size)
+    u32 num_wires, num_routed, num_selectors, num_gate_constants, num_challenges, degree, npp;   // degree = quotient_degree_factor
+    u64 stride;                    // elements between LDE columns (= LDE size L)
+    const u64 *cs, *wires, *zs;    // LDE of constants||sigmas, wires, Z||partial products: [cols][L], bit-reversed rows; the
+                                   // quotient domain is the first 2^log_lq rows (natural LDE indices that are multiples of L / Lq)
+    u64 k_is[PLK_MAX_ROUTED];
+    u64 beta[PLK_MAX_CHALLENGES], gamma[PLK_MAX_CHALLENGES];
+    const u64 *apow;               // plk_fill_apow(alpha): [PLK_MAX_CHALLENGES][apow_stride]
+    u32 apow_stride, first_gate_term;
+    const u64 *l0;                 // [Lq] by position: L_0(x) = Z_H(x) / (n (x - 1))
+    u64 zh_inv[PLK_MAX_ZH];        // 1 / Z_H on the coset: index i mod 2^quotient_degree_bits
+    const u64 *w_lo, *w_hi;        // two-level powers of w_Lq
     u32 w_lo_bits;
-    u64 *out;                      // [num_challenges][L], NATURAL order (input of the coset iNTT)
+    u64 *acc;                      // [num_challenges][Lq] by position
+    u64 *out;                      // [num_challenges][Lq], NATURAL order (input of the coset iNTT)
+    const PlkGateDev *gates;       // device
+    u32 num_gates;
+    PlkGateDev poseidon;           // the natively evaluated gate (valid when has_poseidon)
+    u32 has_poseidon;
+    const u64 *prog, *imm;         // device: programs, immediates (imm[0..4) = public_inputs_hash)
 };
 
-// One LDE point: position `pos` of the bit-reversed storage, natural index i = bitrev(pos).
-GL_HD void quot_point(const QuotParams &p, u64 pos) {
-    const PlkCircuit &C = p.C;
-    const u64 L = (u64)1 << p.log_l;
+GL_HD u64 quot_natural_index(const QuotParams &p, u64 pos) {
+#ifdef __CUDA_ARCH__
+    return p.log_lq ? (__brevll(pos) >> (64 - p.log_lq)) : 0;
+#else
     u64 i = 0;
-    for (u32 b = 0; b < p.log_l; b++) i |= ((pos >> b) & 1) << (p.log_l - 1 - b);
-    const u64 i_next = (i + 8) & (L - 1);
-    u64 pos_next = 0;
-    for (u32 b = 0; b < p.log_l; b++) pos_next |= ((i_next >> b) & 1) << (p.log_l - 1 - b);
+    for (u32 b = 0; b < p.log_lq; b++) i |= ((pos >> b) & 1) << (p.log_lq - 1 - b);
+    return i;
+#endif
+}
+
+// L_0(x)(Z - 1) and the partial-product checks: terms 0 .. first_gate_term of the alpha-sum.
+GL_HD void quot_perm_point(const QuotParams &p, u64 pos) {
+    const u64 Lq = (u64)1 << p.log_lq;
+    const u64 i = quot_natural_index(p, pos);
+    const u64 i_next = (i + (Lq >> p.log_n)) & (Lq - 1);       // multiply x by w_n
+    u64 pos_next;
+    {
+        QuotParams const &q = p;
+#ifdef __CUDA_ARCH__
+        pos_next = q.log_lq ? (__brevll(i_next) >> (64 - q.log_lq)) : 0;
+#else
+        pos_next = 0;
+        for (u32 b = 0; b < q.log_lq; b++) pos_next |= ((i_next >> b) & 1) << (q.log_lq - 1 - b);
+#endif
+    }
     const u64 x = gl_mul(gl_mul(p.w_lo[i & ((1ull << p.w_lo_bits) - 1)], p.w_hi[i >> p.w_lo_bits]), 7);
-    const u32 nc = C.num_selectors + C.num_gate_constants, nch = C.num_challenges;
-    const u32 npp = (C.num_routed + C.quotient_degree_factor - 1) / C.quotient_degree_factor - 1;
-    PlkCols cs = {p.cs, L, pos}, sig = {p.cs + (u64)nc * L, L, pos}, w = {p.wires, L, pos}, zs = {p.zs, L, pos}, zn = {p.zs, L, pos_next};
+    const u32 nc = p.num_selectors + p.num_gate_constants, nch = p.num_challenges, npp = p.npp;
+    PlkCols sig = {p.cs + (u64)nc * p.stride, p.stride, pos}, w = {p.wires, p.stride, pos}, zs = {p.zs, p.stride, pos}, zn = {p.zs, p.stride, pos_next};
     PlkAcc acc;
     for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
-    acc.apow = p.apow; acc.t = 0;
-    // L_0(x) (Z - 1)
-    const u64 l0 = gl_mul(p.zh[i & 7], gl_inverse(gl_mul(p.n_field, gl_sub(x, 1))));
+    acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = 0;
+    const u64 l0 = p.l0[pos];
     for (u32 c = 0; c < nch; c++) plk_emit(acc, gl_mul(l0, gl_sub(zs[c], 1)));
     // partial-product checks, challenge-major.  beta * k_j * x = (beta x) * k_j: one product per wire and challenge
     for (u32 c = 0; c < nch; c++) {
@@ -371,7 +268,7 @@ GL_HD void quot_point(const QuotParams &p, u64 pos) {
             u64 prev = t == 0 ? zs[c] : zs[nch + c * npp + t - 1];
             u64 next = t == npp ? zn[c] : zs[nch + c * npp + t];
             u64 num = 1, den = 1;
-            for (u32 j = t * C.quotient_degree_factor; j < (t + 1) * C.quotient_degree_factor && j < C.num_routed; j++) {
+            for (u32 j = t * p.degree; j < (t + 1) * p.degree && j < p.num_routed; j++) {
                 u64 wv = w[j];
                 num = gl_mul(num, gl_add(gl_mul_add(bx, p.k_is[j], wv), p.gamma[c]));
                 den = gl_mul(den, gl_add(gl_mul_add(p.beta[c], sig[j], wv), p.gamma[c]));
@@ -379,11 +276,107 @@ GL_HD void quot_point(const QuotParams &p, u64 pos) {
             plk_emit(acc, gl_sub(gl_mul(prev, num), gl_mul(next, den)));
         }
     }
-    u64 gate_sum[PLK_MAX_CHALLENGES];
-    plk_gate_constraints(C, w, cs, p.pi_hash, acc, gate_sum);
-    for (u32 c = 0; c < nch; c++) {
-        u64 v = gl_mul(gl_add(acc.sum[c], gate_sum[c]), p.zh_inv[i & 7]);
-        p.out[(u64)c * L + i] = gl_canon(v);
+    for (u32 c = 0; c < nch; c++) p.acc[(u64)c * Lq + pos] = acc.sum[c];
+}
+
+// PoseidonGate, native: acc += filter * sum_t alpha^(first_gate_term + t) c_t
+GL_HD void quot_poseidon_point(const QuotParams &p, u64 pos) {
+    const u64 Lq = (u64)1 << p.log_lq;
+    PlkCols cs = {p.cs, p.stride, pos}, w = {p.wires, p.stride, pos};
+    const PlkGateDev &g = p.poseidon;
+    const u64 filter = plk_filter(g.row, g.group_start, g.group_end, cs[g.selector_index], p.num_selectors > 1);
+    PlkAcc acc;
+    for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
+    acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = p.first_gate_term;
+    plk_poseidon_gate_f64(w, acc);
+    for (u32 c = 0; c < p.num_challenges; c++) {
+        u64 *a = &p.acc[(u64)c * Lq + pos];
+        *a = gl_mul_add(filter, acc.sum[c], *a);
+    }
+}
+
+// Every interpreted gate.  plonky2 adds the gates' filtered constraints per constraint index and then takes powers of
+// alpha; by linearity each gate streams c_t * alpha^(base + t) from the same starting power.
+struct QuotGvmCtx {
+    PlkCols w, k;          // wires; gate constants (after the selector prefix)
+    const u64 *immv;
+    GL_HD u64 wire(u32 i) const { return w[i]; }
+    GL_HD u64 constant(u32 i) const { return k[i]; }
+    GL_HD u64 imm(u32 i) const { return immv[i]; }
+};
+struct QuotGvmEmit {
+    PlkAcc *acc;
+    GL_HD void operator()(u64 v) { plk_emit(*acc, v); }
+};
+GL_HD void quot_gates_point(const QuotParams &p, u64 pos, bool include_native) {
+    const u64 Lq = (u64)1 << p.log_lq;
+    PlkCols cs = {p.cs, p.stride, pos};
+    QuotGvmCtx cx = {{p.wires, p.stride, pos}, {p.cs + (u64)p.num_selectors * p.stride, p.stride, pos}, p.imm};
+    u64 regs[GVM_NREG];
+    u64 total[PLK_MAX_CHALLENGES] = {0, 0};
+    for (u32 gi = 0; gi < p.num_gates; gi++) {
+        const PlkGateDev g = p.gates[gi];
+        if (g.prog_len == 0 || (g.native && !include_native)) continue;
+        const u64 filter = plk_filter(g.row, g.group_start, g.group_end, cs[g.selector_index], p.num_selectors > 1);
+        PlkAcc acc;
+        for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
+        acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = p.first_gate_term;
+        QuotGvmEmit em = {&acc};
+        gvm_run<GvmBaseField>(p.prog + g.prog_off, g.prog_len, cx, regs, em);
+#pragma unroll
+        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) total[c] = gl_mul_add(filter, acc.sum[c], total[c]);
+    }
+    for (u32 c = 0; c < p.num_challenges; c++) {
+        u64 *a = &p.acc[(u64)c * Lq + pos];
+        *a = gl_add(*a, total[c]);
+    }
+}
+
+// * 1 / Z_H(x); position -> natural index
+GL_HD void quot_finish_point(const QuotParams &p, u64 pos) {
+    const u64 Lq = (u64)1 << p.log_lq;
+    const u64 i = quot_natural_index(p, pos);
+    const u64 zi = p.zh_inv[i & ((Lq >> p.log_n) - 1)];
+    for (u32 c = 0; c < p.num_challenges; c++) p.out[(u64)c * Lq + i] = gl_canon(gl_mul(p.acc[(u64)c * Lq + pos], zi));
+}
+
+// L_0 table: l0[pos] = zh[i mod 2^qdb] / (n (x_i - 1)), x_i = 7 w_Lq^i, i = bitrev(pos); 8 positions per thread share one
+// inversion (Montgomery's trick).  x_i != 1 on the coset, so every factor is invertible.
+struct L0Params {
+    u32 log_n, log_lq;
+    u64 n_field;
+    u64 zh[PLK_MAX_ZH];
+    const u64 *w_lo, *w_hi;
+    u32 w_lo_bits;
+    u64 *out;
+};
+#define L0_BATCH 8
+GL_HD void l0_table_group(const L0Params &p, u64 grp) {
+    const u64 Lq = (u64)1 << p.log_lq;
+    u64 d[L0_BATCH], pre[L0_BATCH], idx[L0_BATCH];
+    u64 run = 1;
+    for (int k = 0; k < L0_BATCH; k++) {
+        const u64 pos = grp * L0_BATCH + k;
+        u64 i = 0;
+        if (pos < Lq) {
+#ifdef __CUDA_ARCH__
+            i = p.log_lq ? (__brevll(pos) >> (64 - p.log_lq)) : 0;
+#else
+            for (u32 b = 0; b < p.log_lq; b++) i |= ((pos >> b) & 1) << (p.log_lq - 1 - b);
+#endif
+        }
+        idx[k] = i;
+        const u64 x = gl_mul(gl_mul(p.w_lo[i & ((1ull << p.w_lo_bits) - 1)], p.w_hi[i >> p.w_lo_bits]), 7);
+        d[k] = gl_mul(p.n_field, gl_sub(x, 1));
+        pre[k] = run;
+        run = gl_mul(run, d[k]);
+    }
+    u64 inv = gl_inverse(run);
+    for (int k = L0_BATCH - 1; k >= 0; k--) {
+        const u64 pos = grp * L0_BATCH + k;
+        const u64 dinv = gl_mul(inv, pre[k]);
+        inv = gl_mul(inv, d[k]);
+        if (pos < Lq) p.out[pos] = gl_canon(gl_mul(p.zh[idx[k] & ((Lq >> p.log_n) - 1)], dinv));
     }
 }
 
@@ -392,7 +385,7 @@ struct PpParams {
     u32 log_n, num_routed, num_challenges, degree;   // degree = quotient_degree_factor
     const u64 *wires;     // [num_wires][n] values on the subgroup
     const u64 *sigmas;    // [num_routed][n] values of the sigma polynomials
-    u64 k_is[80];
+    u64 k_is[PLK_MAX_ROUTED];
     u64 beta[PLK_MAX_CHALLENGES], gamma[PLK_MAX_CHALLENGES];
     const u64 *w_lo, *w_hi;   // two-level powers of w_n
     u32 w_lo_bits;
@@ -400,14 +393,16 @@ struct PpParams {
     u64 *row_prod;        // [num_challenges][n]: product of all chunk quotients of the row
 };
 // phase 1: per row, per challenge: the running products of the chunk quotients P_t = prod_{s<=t} q_s (t < npp) go to the
-// partial-product columns, the full row product to row_prod.
+// partial-product columns, the full row product to row_prod.  The chunk denominators of a row and challenge are inverted
+// together: one field inversion + 3 products per chunk (Montgomery's trick).
 GL_HD void pp_row(const PpParams &p, u64 i) {
     const u64 n = (u64)1 << p.log_n;
     const u32 nchunks = (p.num_routed + p.degree - 1) / p.degree, npp = nchunks - 1;
     const u64 x = gl_mul(p.w_lo[i & ((1ull << p.w_lo_bits) - 1)], p.w_hi[i >> p.w_lo_bits]);
     for (u32 c = 0; c < p.num_challenges; c++) {
-        u64 run = 1;
+        u64 nums[PLK_MAX_CHUNKS], dens[PLK_MAX_CHUNKS], pre[PLK_MAX_CHUNKS];
         const u64 bx = gl_mul(p.beta[c], x);
+        u64 run = 1;
         for (u32 t = 0; t < nchunks; t++) {
             u64 num = 1, den = 1;
             for (u32 j = t * p.degree; j < (t + 1) * p.degree && j < p.num_routed; j++) {
@@ -415,7 +410,17 @@ GL_HD void pp_row(const PpParams &p, u64 i) {
                 num = gl_mul(num, gl_add(gl_mul_add(bx, p.k_is[j], wv), p.gamma[c]));
                 den = gl_mul(den, gl_add(gl_mul_add(p.beta[c], p.sigmas[(u64)j * n + i], wv), p.gamma[c]));
             }
-            run = gl_mul(run, gl_mul(num, gl_inverse(den)));
+            nums[t] = num; dens[t] = den; pre[t] = run;
+            run = gl_mul(run, den);
+        }
+        u64 inv = gl_inverse(run);
+        for (u32 t = nchunks; t-- > 0;) {   // nums[t] <- num_t / den_t
+            nums[t] = gl_mul(nums[t], gl_mul(inv, pre[t]));
+            inv = gl_mul(inv, dens[t]);
+        }
+        run = 1;
+        for (u32 t = 0; t < nchunks; t++) {
+            run = gl_mul(run, nums[t]);
             if (t < npp) p.out[((u64)p.num_challenges + (u64)c * npp + t) * n + i] = run;
         }
         p.row_prod[(u64)c * n + i] = run;
@@ -435,10 +440,37 @@ GL_HD void pp_finish(const PpParams &p, u64 i) {
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(128) quotient_kernel(QuotParams p) {
+__global__ void __launch_bounds__(128) quot_perm_kernel(QuotParams p) {
     const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >> p.log_l) return;
-    quot_point(p, pos);
+    if (pos >> p.log_lq) return;
+    quot_perm_point(p, pos);
+}
+__global__ void __launch_bounds__(128) quot_poseidon_kernel(QuotParams p) {
+    const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >> p.log_lq) return;
+    quot_poseidon_point(p, pos);
+}
+__global__ void __launch_bounds__(128) quot_gates_kernel(QuotParams p, int include_native) {
+    const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >> p.log_lq) return;
+    quot_gates_point(p, pos, include_native != 0);
+}
+__global__ void __launch_bounds__(256) quot_finish_kernel(QuotParams p) {
+    const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >> p.log_lq) return;
+    quot_finish_point(p, pos);
+}
+__global__ void __launch_bounds__(128) l0_table_kernel(L0Params p) {
+    const u64 grp = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((grp * L0_BATCH) >> p.log_lq) return;
+    l0_table_group(p, grp);
+}
+// flag |= any non-zero element in [first, first + count) of each of `cols` columns (stride elements apart)
+__global__ void __launch_bounds__(256) nonzero_flag_kernel(const u64 *data, u64 stride, u32 cols, u64 first, u64 count, u32 *flag) {
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    for (u32 c = 0; c < cols; c++)
+        if (gl_canon(data[(u64)c * stride + first + k]) != 0) { *flag = 1; return; }
 }
 __global__ void __launch_bounds__(128) pp_row_kernel(PpParams p) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;

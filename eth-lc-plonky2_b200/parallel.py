@@ -84,6 +84,11 @@ class EngineOps:
                                      C.c_void_p(coeffs_out.data_ptr()), C.c_void_p(lde_out.data_ptr())))
         _lib.synchronize()   # the exchange runs on torch's stream
 
+    def after_exchange(self):
+        """The exchange (all_to_all_single / copy_) was enqueued on torch's current stream and returns at once; the leaf
+        hashing runs on the ENGINE's stream, which has no dependency on it.  Wait for the exchange before hashing."""
+        self.torch.cuda.current_stream(self.device).synchronize()
+
     def merkle(self, rows_colmajor, num_polys, num_rows, cap_height):
         from .plonky2 import MerkleTree, _Handle
         h = C.c_void_p()
@@ -105,16 +110,26 @@ class _DevArray:
 
 
 class PeerExchange:
-    """Receive side of the fused exchange for one ShardPlan: this rank's [C][L/G] leaf matrix (allocated outside the pool,
-    exported over CUDA IPC) and the peer mappings of everybody else's.  Collective constructor; reusable across steps."""
+    """Receive side of the fused exchange for one ShardPlan: this rank's [C][L/G] leaf matrices (allocated outside the pool,
+    exported over CUDA IPC) and the peer mappings of everybody else's.  Collective constructor; reusable across steps.
 
-    def __init__(self, plan, rank, device, group=None, dist=None):
+    `slots` leaf matrices form a ring: a batch built in slot s keeps referring to that matrix (its `rows` and the leaves
+    behind MerkleTree::get are views of it, not copies), so a prover that keeps several oracles alive (wires, Z, quotient
+    ... until the FRI query phase) gives each its own slot.  Every from_values bumps the slot's generation; accessors of an
+    older batch of the same slot raise instead of returning rows that no longer match their digests."""
+
+    def __init__(self, plan, rank, device, group=None, dist=None, slots=1):
         import torch
         if dist is None:
             import torch.distributed as dist
         self.plan, self.rank, self.group, self.dist = plan, rank, group, dist
         lib = _lib.lib()
-        elems = plan.num_polys * plan.rows_per_rank
+        if slots < 1:
+            raise EngineError(_lib.ENG_ERR_INVALID, "PeerExchange needs at least one slot")
+        self.slots = slots
+        self.slot_elems = plan.num_polys * plan.rows_per_rank
+        self.generation = [0] * slots
+        elems = self.slot_elems * slots
         self.local_ptr, self.bases, self._opened = None, [], []
         self._token = torch.zeros(1, dtype=torch.int32, device=device)
         ptr = C.c_void_p()
@@ -143,8 +158,22 @@ class PeerExchange:
             err = e
         self._agree(err, "mapping the peers' exchange buffers (CUDA IPC / peer access)")
         off = plan.col_offsets[rank] * plan.rows_per_rank * 8     # this rank's first column inside every leaf matrix
-        self.shard_out = (C.c_void_p * plan.world)(*[b + off for b in self.bases])
-        self.recv = torch.as_tensor(_DevArray(self.local_ptr, elems), device=device)
+        self._shard_out = [(C.c_void_p * plan.world)(*[b + s * self.slot_elems * 8 + off for b in self.bases]) for s in range(slots)]
+        self._recv = torch.as_tensor(_DevArray(self.local_ptr, elems), device=device).view(slots, self.slot_elems)
+
+    @property
+    def shard_out(self):
+        return self._shard_out[0]
+
+    @property
+    def recv(self):
+        return self._recv[0]
+
+    def slot_shard_out(self, slot):
+        return self._shard_out[slot]
+
+    def slot_recv(self, slot):
+        return self._recv[slot]
 
     def _agree(self, err, what):
         """Collective: raises on EVERY rank if any rank failed."""
@@ -186,14 +215,29 @@ class PeerExchange:
 class ShardedPolynomialBatch:
     """PolynomialBatch whose polynomials are column-sharded and whose leaves / digests are row-sharded."""
 
-    def __init__(self, plan, rank, coeffs, rows, tree, cap, ops):
-        self.plan, self.rank, self.coeffs, self.rows, self.merkle_tree_local, self.cap, self.ops = plan, rank, coeffs, rows, tree, cap, ops
+    def __init__(self, plan, rank, coeffs, rows, tree, cap, ops, exchange=None, slot=0):
+        self.plan, self.rank, self.coeffs, self._rows, self.merkle_tree_local, self.cap, self.ops = plan, rank, coeffs, rows, tree, cap, ops
+        # with a PeerExchange the leaves live in the exchange's slot (not owned): valid until the slot is reused
+        self._exchange, self._slot = exchange, slot
+        self._generation = exchange.generation[slot] if exchange is not None else 0
+
+    def _check_live(self):
+        if self._exchange is not None and self._exchange.generation[self._slot] != self._generation:
+            raise EngineError(_lib.ENG_ERR_STATE, "the leaf matrix of this batch (exchange slot %d) was overwritten by a later "
+                              "from_values; give every live batch its own slot (PeerExchange(slots=k))" % self._slot)
+
+    @property
+    def rows(self):
+        """This rank's leaves, column-major [C][L/G] (a view of the exchange slot when the fused exchange built them)."""
+        self._check_live()
+        return self._rows
 
     @classmethod
-    def from_values(cls, local_values, plan, rank, group=None, ops=None, is_values=True, dist=None, exchange=None):
+    def from_values(cls, local_values, plan, rank, group=None, ops=None, is_values=True, dist=None, exchange=None, slot=0):
         """local_values: [plan.col_counts[rank]][2^log_n] tensor holding this rank's columns (values, or coefficients
         when is_values is False).  Collective over `group` (torch.distributed).  With `exchange` (a PeerExchange of the
-        same plan) the column->row exchange is fused into the LDE's last pass; its leaf matrix is reused by every call."""
+        same plan) the column->row exchange is fused into the LDE's last pass; the leaves land in leaf matrix `slot` of the
+        exchange, which the returned batch refers to until a later call reuses that slot."""
         if dist is None:
             import torch.distributed as dist
         if ops is None and not isinstance(local_values, (list, tuple)):
@@ -216,23 +260,27 @@ class ShardedPolynomialBatch:
             import os, time
             trace = os.environ.get("ENG_TRACE")
             t0 = time.perf_counter()
+            if not 0 <= slot < exchange.slots:
+                raise EngineError(_lib.ENG_ERR_INVALID, "exchange slot %d out of range (%d slots)" % (slot, exchange.slots))
             scratch = ops.empty(c_r * (n << plan.rate_bits))
+            exchange.generation[slot] += 1           # earlier batches of this slot are dead from here on
+            shard_out = exchange.slot_shard_out(slot)
             exchange.barrier()                       # every rank has finished reading its leaf matrix of the previous call
             t1 = time.perf_counter()
             if host_cols is not None:
                 ptrs = (C.c_void_p * c_r)(*[c.ctypes.data for c in host_cols])
                 check(_lib.lib().eng_lde_peer_host(ptrs, c_r, plan.log_n, plan.rate_bits, int(is_values), plan.log_world,
-                                                   C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), exchange.shard_out, rank))
+                                                   C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), shard_out, rank))
             else:
                 check(_lib.lib().eng_lde_peer_dev(C.c_void_p(local_values.data_ptr()), c_r, plan.log_n, plan.rate_bits, int(is_values),
                                                   plan.log_world, C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()),
-                                                  exchange.shard_out, rank))
+                                                  shard_out, rank))
             _lib.synchronize()
             t2 = time.perf_counter()
             exchange.barrier()                       # every rank's stores have landed
             t3 = time.perf_counter()
             del scratch
-            recv = exchange.recv
+            recv = exchange.slot_recv(slot)
             tree = ops.merkle(recv, plan.num_polys, plan.rows_per_rank, plan.local_cap_height)
             local_cap = ops.to_tensor(tree.cap).reshape(-1)
             t4 = time.perf_counter()
@@ -242,7 +290,7 @@ class ShardedPolynomialBatch:
             if trace:
                 print("rank %d: alloc+barrier %.1f  lde %.1f  barrier %.1f  merkle+cap %.1f  gather %.1f ms" % (
                     rank, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3), 1e3 * (time.perf_counter() - t4)), flush=True)
-            return cls(plan, rank, coeffs, recv.view(plan.num_polys, plan.rows_per_rank), tree, cap, ops)
+            return cls(plan, rank, coeffs, recv.view(plan.num_polys, plan.rows_per_rank), tree, cap, ops, exchange, slot)
         send = ops.empty(c_r * (n << plan.rate_bits))
         ops.lde(local_values, is_values, plan.log_n, plan.rate_bits, plan.log_world, coeffs, send)   # [G][C_r][L/G]
         recv = ops.empty(plan.num_polys * plan.rows_per_rank)                                          # [C][L/G]
@@ -250,6 +298,7 @@ class ShardedPolynomialBatch:
             dist.all_to_all_single(recv, send, output_split_sizes=plan.recv_splits(), input_split_sizes=plan.send_splits(rank), group=group)
         else:
             recv.copy_(send)
+        getattr(ops, "after_exchange", lambda: None)()     # torch stream -> engine stream ordering (see EngineOps)
         del send
         tree = ops.merkle(recv, plan.num_polys, plan.rows_per_rank, plan.local_cap_height)
         local_cap = ops.to_tensor(tree.cap).reshape(-1)
@@ -270,6 +319,7 @@ class ShardedPolynomialBatch:
         owner, local = self.plan.owner_of_leaf(leaf_index)
         if owner != self.rank:
             raise EngineError(_lib.ENG_ERR_INVALID, "leaf %d lives on rank %d" % (leaf_index, owner))
+        self._check_live()
         return self.merkle_tree_local.get(local)
 
     def prove(self, leaf_index):

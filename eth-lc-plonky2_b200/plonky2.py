@@ -183,7 +183,8 @@ class PolynomialBatch:
 
     @classmethod
     def from_values(cls, values, rate_bits, blinding, cap_height, timing=None, fft_root_table=None, blinding_seed=0):
-        """PolynomialBatch::from_values(values: Vec<PolynomialValues<F>>, rate_bits, blinding, cap_height, ..)."""
+        """PolynomialBatch::from_values(values: Vec<PolynomialValues<F>>, rate_bits, blinding, cap_height, ..).
+        blinding_seed = 0 (the default): salts keyed from the OS RNG, as plonky2's OsRng; non-zero: reproducible test stream."""
         return cls._make(values, rate_bits, blinding, cap_height, True, blinding_seed)
 
     @classmethod
@@ -388,7 +389,20 @@ PolynomialBatch.eval = _eval_batch
 PolynomialBatch.prove_openings = staticmethod(_prove_openings)
 
 
-# ---------------------------------------------------------------- a5 / a6 / prove
+# ---------------------------------------------------------------- a5 / a6 / prove / verify
+GATE_KINDS = ("Noop", "Constant", "PublicInput", "Arithmetic", "Poseidon", "BaseSum", "ArithmeticExtension", "MulExtension", "Reducing",
+              "ReducingExtension", "RandomAccess", "Exponentiation", "PoseidonMds", "U32Arithmetic", "U32AddMany", "U32Subtraction",
+              "U32RangeCheck", "Comparison")
+BLOB_V2_MAGIC = 0x32424B4C50
+ALL_GATES = (1 << len(GATE_KINDS)) - 1
+
+
+def _take_blob(ptr, n):
+    out = np.ctypeslib.as_array(ptr, shape=(n.value,)).copy()
+    _lib.load().eng_blob_free(ptr)
+    return out
+
+
 def synth_circuit(degree_bits, seed=1):
     """Synthetic circuit over the five core gates with a satisfying witness (eng_synth_circuit; host code, no GPU).
     Returns dict(blob, constants [4][n], sigmas [80][n], wires [135][n], pi_hash [4])."""
@@ -400,30 +414,110 @@ def synth_circuit(degree_bits, seed=1):
     return out
 
 
+def synth_circuit_v2(degree_bits, seed=1, kinds_mask=ALL_GATES):
+    """Synthetic circuit over the gates of `kinds_mask` (bit k = GATE_KINDS[k]; default: all 18) with a satisfying witness,
+    selector groups formed by plonky2's rule, version-2 description with the gates' bytecode (eng_synth_circuit_v2; host code)."""
+    n = 1 << degree_bits
+    consts = np.zeros((8, n), np.uint64)
+    out = dict(sigmas=np.zeros((80, n), np.uint64), wires=np.zeros((135, n), np.uint64), pi_hash=np.zeros(4, np.uint64))
+    nc = C.c_uint32(0)
+    blob = C.POINTER(C.c_uint64)()
+    blen = C.c_size_t(0)
+    check(_lib.load().eng_synth_circuit_v2(degree_bits, seed, kinds_mask, ptr(consts), ptr(out["sigmas"]), ptr(out["wires"]),
+                                           ptr(out["pi_hash"]), C.byref(nc), C.byref(blob), C.byref(blen)))
+    out["constants"] = consts[:nc.value].copy()
+    out["blob"] = _take_blob(blob, blen)
+    return out
+
+
+def circuit_describe(header12, gates8, digest4):
+    """eng_circuit_describe: version-2 description (with bytecode) of a circuit over library gates."""
+    h, g_, d = host_u64(header12), host_u64(gates8).reshape(-1, 8), host_u64(digest4)
+    blob = C.POINTER(C.c_uint64)()
+    blen = C.c_size_t(0)
+    check(_lib.load().eng_circuit_describe(ptr(h), ptr(g_), g_.shape[0], ptr(d), C.byref(blob), C.byref(blen)))
+    return _take_blob(blob, blen)
+
+
 def _col_ptrs(cols):
     cols = [host_u64(c) for c in cols]
     return cols, (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
 
 
+def verify(circuit_blob, constants_sigmas_cap, public_inputs_hash, proof_blob):
+    """CircuitData::verify (host code, no device needed).  Returns None when the proof verifies; raises EngineError
+    (ENG_ERR_INVALID, message = the failed check) otherwise, as plonky2's verify() returns Err."""
+    b, cap, pi, pr = host_u64(circuit_blob), host_u64(constants_sigmas_cap).ravel(), host_u64(public_inputs_hash), host_u64(proof_blob)
+    check(_lib.load().eng_verify(ptr(b), ptr(cap), ptr(pi), ptr(pr), pr.size))
+
+
+def proof_to_bytes(circuit_blob, proof_blob, public_inputs=()):
+    """ProofWithPublicInputs::to_bytes (plonky2's wire format as restated; see include/plonky2_b200.h)."""
+    b, pr, pis = host_u64(circuit_blob), host_u64(proof_blob), host_u64(list(public_inputs))
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t(0)
+    check(_lib.load().eng_proof_to_bytes(ptr(b), ptr(pr), pr.size, ptr(pis), pis.size, C.byref(out), C.byref(n)))
+    data = bytes(bytearray(out[:n.value]))
+    _lib.load().eng_bytes_free(out)
+    return data
+
+
+def proof_from_bytes(circuit_blob, data):
+    """ProofWithPublicInputs::from_bytes -> (proof blob, public inputs)."""
+    b = host_u64(circuit_blob)
+    buf = np.frombuffer(data, np.uint8).copy()
+    pb, pi = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)()
+    pn, qn = C.c_size_t(0), C.c_size_t(0)
+    check(_lib.load().eng_proof_from_bytes(ptr(b), ptr(buf), buf.size, C.byref(pb), C.byref(pn), C.byref(pi), C.byref(qn)))
+    proof = _take_blob(pb, pn)
+    pis = np.ctypeslib.as_array(pi, shape=(max(qn.value, 1),))[:qn.value].copy()
+    _lib.load().eng_blob_free(pi)
+    return proof, pis
+
+
 class Circuit:
     """What the plonk rows need of plonky2's CommonCircuitData / ProverOnlyCircuitData, resident on the device."""
 
-    def __init__(self, blob, constants_sigmas, sigma_values):
+    def __init__(self, blob, constants_sigmas, sigma_values, _handle=None):
         self.blob = host_u64(blob)
-        b = [int(x) for x in self.blob]
-        (self.degree_bits, self.num_wires, self.num_routed, self.num_gate_constants, self.num_selectors, self.num_challenges,
-         self.quotient_degree_factor, self.rate_bits, self.cap_height) = b[:9]
-        self.num_partial_products = (self.num_routed + self.quotient_degree_factor - 1) // self.quotient_degree_factor - 1
         self.constants_sigmas = constants_sigmas
-        keep, ptrs = _col_ptrs(sigma_values)
-        self._h = C.c_void_p()
-        check(_lib.lib().eng_circuit_new(ptr(self.blob), constants_sigmas._o._h, ptrs, C.byref(self._h)))
+        if _handle is None:
+            keep, ptrs = _col_ptrs(sigma_values)
+            self._h = C.c_void_p()
+            check(_lib.lib().eng_circuit_new(ptr(self.blob), constants_sigmas._o._h, ptrs, C.byref(self._h)))
+        else:
+            self._h = _handle
+        info = _lib.CircuitInfo()
+        check(_lib.lib().eng_circuit_info(self._h, C.byref(info)))
+        self.info = info
+        self.degree_bits, self.num_wires, self.num_routed = info.degree_bits, info.num_wires, info.num_routed_wires
+        self.num_selectors, self.num_challenges, self.quotient_degree_factor = info.num_selectors, info.num_challenges, info.quotient_degree_factor
+        self.num_gate_constants = info.num_constants - info.num_selectors
+        self.rate_bits, self.cap_height, self.num_partial_products = info.rate_bits, info.cap_height, info.num_partial_products
 
     @classmethod
     def build(cls, synth, rate_bits=3, cap_height=4):
         """The part of CircuitBuilder::build() on the hot path: commit constants || sigmas."""
         cs = PolynomialBatch.from_values(list(synth["constants"]) + list(synth["sigmas"]), rate_bits, False, cap_height)
         return cls(synth["blob"], cs, synth["sigmas"])
+
+    def save(self, path):
+        """eng_circuit_save: the prover-data cache (description, constant / sigma polynomials, cap)."""
+        check(_lib.lib().eng_circuit_save(self._h, ptr(self.blob), str(path).encode()))
+
+    @classmethod
+    def load(cls, path):
+        """eng_circuit_load: rebuilds the constants||sigmas commitment on the GPU from the cache file."""
+        h = C.c_void_p()
+        blob = C.POINTER(C.c_uint64)()
+        blen = C.c_size_t(0)
+        check(_lib.lib().eng_circuit_load(str(path).encode(), C.byref(h), C.byref(blob), C.byref(blen)))
+        b = _take_blob(blob, blen)
+        cs = C.c_void_p()
+        check(_lib.lib().eng_circuit_constants_sigmas(h, C.byref(cs)))
+        owner = _Handle(cs)
+        owner.close = lambda: None          # the circuit handle owns this batch
+        return cls(b, PolynomialBatch(owner), None, _handle=h)
 
     def partial_products(self, wire_values, betas, gammas):
         """all_wires_permutation_partial_products -> [num_challenges*(1+num_partial_products)][n], committed order."""
@@ -435,7 +529,7 @@ class Circuit:
         return out
 
     def quotient(self, wires_batch, zs_pp_batch, public_inputs_hash, betas, gammas, alphas):
-        """compute_quotient_polys + split + commit -> PolynomialBatch of num_challenges*8 chunk polynomials."""
+        """compute_quotient_polys + split + commit -> PolynomialBatch of num_challenges*quotient_degree_factor chunk polynomials."""
         h = C.c_void_p()
         pi, b, g_, a = host_u64(public_inputs_hash), host_u64(betas), host_u64(gammas), host_u64(alphas)
         check(_lib.lib().eng_quotient(self._h, wires_batch._o._h, zs_pp_batch._o._h, ptr(pi), ptr(b), ptr(g_), ptr(a), C.byref(h)))
@@ -449,11 +543,14 @@ class Circuit:
         n = C.c_size_t(0)
         ms = (C.c_float * 8)()
         check(_lib.lib().eng_prove(self._h, ptrs, ptr(pi), C.byref(blob), C.byref(n), ms))
-        out = np.ctypeslib.as_array(blob, shape=(n.value,)).copy()
-        _lib.lib().eng_blob_free(blob)
+        out = _take_blob(blob, n)
         names = ("wires commitment", "partial products", "Z commitment", "quotient polys", "quotient commitment", "opening set",
                  "opening proofs (FRI)", "total")
         return out, dict(zip(names, list(ms)))
+
+    def verify(self, public_inputs_hash, proof_blob):
+        """data.verify(proof): raises EngineError when the proof is rejected."""
+        verify(self.blob, self.constants_sigmas.merkle_tree.cap, public_inputs_hash, proof_blob)
 
     def __del__(self):
         try:

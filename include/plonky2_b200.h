@@ -48,6 +48,11 @@ eng_status eng_synchronize(void);
  * stream-ordered pool's unused memory, to the driver. */
 eng_status eng_release_cached(void);
 eng_status eng_launch_count(uint64_t *out);       /* kernels launched by the engine since eng_init */
+/* Engine options (A/B switches used by tests and profiles; defaults are the product path):
+ *   "quot_native_poseidon" 1  PoseidonGate through the native FP64 evaluator (0: through its bytecode, like every other gate)
+ *   "lde_group_mb"         48 megabytes of LDE a (columns x cosets) group may hold between the two passes of the transform
+ *                             so that the second pass reads it from L2 (0: one launch per pass over the whole batch) */
+eng_status eng_set_option(const char *name, int64_t value);
 
 /* Measured integer issue rates of this device, thread-operations per second:
  * [0] 32-bit IMAD (mad.lo.u32)  [1] IMAD.WIDE (mad.wide.u32)  [2] alu-pipe ops (add/xor).  The roofline denominators
@@ -64,7 +69,9 @@ eng_status eng_two_to_one(const uint64_t *pairs_host, size_t count, uint64_t *ou
 
 /* ---- a1/a2: PolynomialBatch::from_values / from_coeffs  [plonky2:fri/oracle.rs] ----
  * cols_host[c] points at polynomial c (2^log_n elements).  blinding != 0 appends SALT_SIZE = 4 random leaf
- * elements per row (plonky2 draws them from OsRng; here a SplitMix64 stream seeded with blinding_seed).
+ * elements per row.  plonky2 draws them from OsRng; here they are the ChaCha20 key stream under a fresh 256-bit key taken
+ * from the OS random number generator (getrandom) for every batch: blinding_seed MUST be 0 for that.  A non-zero
+ * blinding_seed derives the key from the seed instead -- reproducible, for tests only, NOT hiding.
  * timing / fft_root_table of the Rust signature have no counterpart: stage times are read back with
  * eng_batch_stage_ms, root tables are cached inside the engine. */
 eng_status eng_batch_from_values(const uint64_t *const *cols_host, uint32_t num_polys, uint32_t log_n,
@@ -181,17 +188,49 @@ eng_status eng_fri_prove_openings(const uint64_t *instance, const eng_batch *con
 eng_status eng_blob_free(uint64_t *blob);
 
 /* ---- circuit handle for the plonk rows ----
- * blob (what the rows need of CommonCircuitData / ProverOnlyCircuitData): [degree_bits, num_wires, num_routed_wires,
- *   num_constants (gate constants, without selectors), num_selectors, num_challenges, quotient_degree_factor, rate_bits,
- *   cap_height, proof_of_work_bits, num_query_rounds, num_gates, (gate_kind, selector_index, group.start, group.end)
- *   x num_gates (gates in plonky2's degree-sorted order), circuit_digest x 4].
- * gate_kind: 0 NoopGate, 1 ConstantGate{2}, 2 PublicInputGate, 3 ArithmeticGate{20}, 4 PoseidonGate.
+ * blob: what the rows need of CommonCircuitData / ProverOnlyCircuitData.  Two layouts are accepted.
+ * Version 2 (gates are DATA -- any gate set, see csrc/gate_vm.h and INTEGRATION.md):
+ *   [0] 0x32424B4C50 ("PLKB2")  [1] total length in words
+ *   [2..14) degree_bits, num_wires, num_routed_wires, num_constants (gate constants, without selectors), num_selectors,
+ *           num_challenges, quotient_degree_factor, rate_bits, cap_height, proof_of_work_bits, num_query_rounds, num_gates
+ *   [14] num_imm  [15] prog_words  [16..20) circuit_digest
+ *   num_gates x 12 words (gates in plonky2's degree-sorted order; the index of a gate is the selector value enabling it):
+ *     kind, selector_index, group.start, group.end, p0, p1, p2, p3, num_constraints, prog_offset, prog_len, 0
+ *   prog_words instruction words (the gates' eval_unfiltered as straight-line programs: add / sub / mul / mad / msub / mov /
+ *     emit over wires, gate constants, immediates and 64 registers)   |   num_imm immediates (the first 4 are reserved for
+ *     public_inputs_hash).
+ *   kind names the gate for the library (prog_len = 0: the program is built by csrc/gate_lib.h): 0 Noop, 1 Constant{p0},
+ *   2 PublicInput, 3 Arithmetic{p0 ops}, 4 Poseidon, 5 BaseSum<p0>{p1 limbs}, 6 ArithmeticExtension{p0}, 7 MulExtension{p0},
+ *   8 Reducing{p0 coeffs}, 9 ReducingExtension{p0}, 10 RandomAccess{p0 bits, p1 copies, p2 extra constants},
+ *   11 Exponentiation{p0 bits}, 12 PoseidonMds, 13 U32Arithmetic{p0}, 14 U32AddMany{p0 addends, p1 ops}, 15 U32Subtraction{p0},
+ *   16 U32RangeCheck{p0 limbs}, 17 Comparison{p0 bits, p1 chunks}; 255 = custom (the program is mandatory).
+ * Version 1 (the five core gates, kept for round-1 callers): the 12 header words, (kind, selector_index, group.start,
+ *   group.end) x num_gates, circuit_digest x 4.
  * constants_sigmas: the batch committed by build() (selectors, gate constants, sigmas -- in that column order);
  * sigma_cols_host: the sigma polynomials' values on the subgroup (prover_data.sigmas, column j = routed wire j). */
 typedef struct eng_circuit eng_circuit;
 eng_status eng_circuit_new(const uint64_t *blob, const eng_batch *constants_sigmas, const uint64_t *const *sigma_cols_host,
                            eng_circuit **out);
 eng_status eng_circuit_free(eng_circuit *c);
+typedef struct {
+    uint32_t degree_bits, num_wires, num_routed_wires, num_constants /* selectors + gate constants */, num_selectors,
+             num_challenges, quotient_degree_factor, num_partial_products, rate_bits, cap_height, num_gates,
+             num_gate_constraints;
+} eng_circuit_info_t;
+eng_status eng_circuit_info(const eng_circuit *c, eng_circuit_info_t *out);
+/* Version-2 description of a circuit whose gates the library knows.  header12: the 12 header words above; gates8: num_gates x
+ * (kind, selector_index, group.start, group.end, p0, p1, p2, p3); digest4: circuit_digest.  *blob_out: malloc'ed
+ * (eng_blob_free).  Host code, no device needed. */
+eng_status eng_circuit_describe(const uint64_t *header12, const uint64_t *gates8, uint32_t num_gates, const uint64_t *digest4,
+                                uint64_t **blob_out, size_t *blob_len);
+/* ---- f2: prover-data cache (CircuitBuilder::build()'s constants||sigmas commitment, not re-paid per process) ----
+ * eng_circuit_save writes the circuit description, the constant / sigma polynomials and the cap of their commitment to
+ * `path`; eng_circuit_load rebuilds the device-resident commitment from them (LDE + Merkle tree on the GPU, checked against
+ * the stored cap) and returns a circuit handle that owns it. */
+eng_status eng_circuit_save(const eng_circuit *c, const uint64_t *blob, const char *path);
+eng_status eng_circuit_load(const char *path, eng_circuit **out, uint64_t **blob_out, size_t *blob_len);
+/* the constants||sigmas batch a circuit handle refers to (owned by the handle after eng_circuit_load) */
+eng_status eng_circuit_constants_sigmas(const eng_circuit *c, const eng_batch **out);
 
 /* ---- a5: all_wires_permutation_partial_products  [plonky2:plonk/prover.rs] ----
  * wire_cols_host: the full witness (num_wires columns, only the routed ones are read).  out_host:
@@ -214,11 +253,36 @@ eng_status eng_quotient(const eng_circuit *c, const eng_batch *wires, const eng_
 eng_status eng_prove(const eng_circuit *c, const uint64_t *const *wire_cols_host, const uint64_t *public_inputs_hash,
                      uint64_t **blob_out, size_t *blob_len, float *stage_ms);
 
-/* Synthetic circuit (tests / bench input generator, host code): 2^degree_bits rows of the five core gates with a
- * satisfying witness and non-trivial copy constraints.  Caller-allocated outputs, column-major: constants [4][n]
- * (selector 0, selector 1, gate constants 0 and 1), sigmas [80][n], wires [135][n], pi_hash [4], circuit_blob [36]. */
+/* ---- f4: CircuitData::verify and ProofWithPublicInputs::{to_bytes, from_bytes}  [plonky2:plonk/verifier.rs,
+ * util/serialization]; reached from /root/reference/eth-lc-plonky2/src/main.rs:233 ----
+ * Host code, as in the reference (verification is a few hundred permutations): no device and no eng_init needed.
+ * circuit_blob: the circuit description (either version); constants_sigmas_cap: verifier_only.constants_sigmas_cap
+ * (2^cap_height x 4); proof_blob: as returned by eng_prove.  ENG_OK = the proof verifies; ENG_ERR_INVALID = rejected, with
+ * the failing check in eng_last_error (the Rust shim turns that into verify()'s Err). */
+eng_status eng_verify(const uint64_t *circuit_blob, const uint64_t *constants_sigmas_cap, const uint64_t *public_inputs_hash,
+                      const uint64_t *proof_blob, size_t proof_len);
+/* plonky2's wire format as restated (to be re-checked against the source): little-endian
+ * canonical u64 per field element, caps / openings / FRI layers in struct order without length prefixes, one byte of
+ * sibling count in front of every Merkle proof, the public inputs last.  *bytes_out: malloc'ed (eng_bytes_free). */
+eng_status eng_proof_to_bytes(const uint64_t *circuit_blob, const uint64_t *proof_blob, size_t proof_len, const uint64_t *public_inputs,
+                              size_t num_public_inputs, uint8_t **bytes_out, size_t *bytes_len);
+eng_status eng_proof_from_bytes(const uint64_t *circuit_blob, const uint8_t *bytes, size_t bytes_len, uint64_t **proof_blob_out,
+                                size_t *proof_len, uint64_t **public_inputs_out, size_t *num_public_inputs);
+eng_status eng_bytes_free(uint8_t *bytes);
+
+/* Synthetic circuits (tests / bench input generators, host code): 2^degree_bits rows of plonky2 gates with a satisfying
+ * witness and non-trivial copy constraints.  Caller-allocated outputs, column-major.
+ * Version 1: the five core gates; constants [4][n] (selector 0, selector 1, gate constants 0 and 1), sigmas [80][n], wires
+ * [135][n], pi_hash [4], circuit_blob [36] (version-1 layout). */
 eng_status eng_synth_circuit(uint32_t degree_bits, uint64_t seed, uint64_t *constants, uint64_t *sigmas, uint64_t *wires,
                              uint64_t *pi_hash, uint64_t *circuit_blob);
+/* Version 2: the gates selected by kinds_mask (bit k = gate kind k of the list above; Noop and PublicInput always), sorted by
+ * degree and grouped into selector polynomials by plonky2's greedy rule.  constants: [ENG_SYNTH_MAX_CONSTANTS][n] of which
+ * the first *num_constants columns are used (selectors, then the two gate constants); *blob_out: malloc'ed version-2
+ * description (eng_blob_free). */
+#define ENG_SYNTH_MAX_CONSTANTS 8
+eng_status eng_synth_circuit_v2(uint32_t degree_bits, uint64_t seed, uint64_t kinds_mask, uint64_t *constants, uint64_t *sigmas,
+                                uint64_t *wires, uint64_t *pi_hash, uint32_t *num_constants, uint64_t **blob_out, size_t *blob_len);
 
 #ifdef __cplusplus
 }

@@ -154,14 +154,24 @@ void orc_challenger_state(void *c, u64 *out /* 12 state + 1 n_in + 8 in + 1 n_ou
  * circuit blob: [degree_bits, num_wires, num_routed, num_gate_constants, num_selectors, num_challenges,
  *   quotient_degree_factor, rate_bits, cap_height, pow_bits, num_query_rounds, num_gates,
  *   (kind, selector_index, group_start, group_end) x num_gates, circuit_digest x 4] */
-void *orc_circuit_new(const u64 *b) {
+/* Both layouts of include/plonky2_b200.h.  From a version-2 description the oracle reads the gate KINDS and parameters only:
+ * the bytecode programs in it are what the engine runs, the oracle evaluates the gates from its own formulas (gates.h). */
+void *orc_circuit_new(const u64 *b0) {
     OrcCircuit *c = new OrcCircuit();
+    const bool v2 = b0[0] == 0x32424B4C50ULL;
+    const u64 *b = v2 ? b0 + 2 : b0;
     c->degree_bits = (int)b[0]; c->num_wires = (int)b[1]; c->num_routed = (int)b[2]; c->num_gate_constants = (int)b[3];
     c->num_selectors = (int)b[4]; c->num_challenges = (int)b[5]; c->quotient_degree_factor = (int)b[6]; c->rate_bits = (int)b[7];
     c->cap_height = (int)b[8]; c->pow_bits = (int)b[9]; c->num_query_rounds = (int)b[10];
     int ng = (int)b[11];
-    for (int i = 0; i < ng; i++) { OrcGateInfo g = {(int)b[12 + 4 * i], (int)b[13 + 4 * i], (int)b[14 + 4 * i], (int)b[15 + 4 * i]}; c->gates.push_back(g); }
-    for (int i = 0; i < 4; i++) c->circuit_digest[i] = gl_canon(b[12 + 4 * ng + i]);
+    for (int i = 0; i < ng; i++) {
+        const u64 *e = v2 ? b0 + 20 + 12 * i : b + 12 + 4 * i;
+        OrcGateInfo g = {(int)e[0], (int)e[1], (int)e[2], (int)e[3], {0, 0, 0, 0}};
+        if (v2) for (int k = 0; k < 4; k++) g.p[k] = (int)e[4 + k];
+        else { if (g.kind == ORC_G_CONSTANT) g.p[0] = 2; if (g.kind == ORC_G_ARITHMETIC) g.p[0] = 20; }
+        c->gates.push_back(g);
+    }
+    for (int i = 0; i < 4; i++) c->circuit_digest[i] = gl_canon(v2 ? b0[16 + i] : b[12 + 4 * ng + i]);
     u64 k = 1;
     for (int j = 0; j < c->num_routed; j++) { c->k_is.push_back(k); k = gl_mul(k, GL_GENERATOR); }
     return c;

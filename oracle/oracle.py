@@ -289,6 +289,8 @@ class Circuit:
         self.blob = _a(blob)
         self.h = lib().orc_circuit_new(self.blob)
         b = [int(x) for x in self.blob]
+        if b[0] == 0x32424B4C50:     # version-2 description: header after [magic, length]
+            b = b[2:]
         (self.degree_bits, self.num_wires, self.num_routed, self.num_gate_constants, self.num_selectors, self.num_challenges,
          self.quotient_degree_factor, self.rate_bits, self.cap_height) = b[:9]
         self.num_pp = (self.num_routed + self.quotient_degree_factor - 1) // self.quotient_degree_factor - 1

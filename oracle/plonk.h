@@ -15,11 +15,14 @@
 #ifndef ORACLE_PLONK_H
 #define ORACLE_PLONK_H
 #include "fri.h"
+#include "gates.h"
 
 enum { ORC_G_NOOP = 0, ORC_G_CONSTANT = 1, ORC_G_PUBLIC_INPUT = 2, ORC_G_ARITHMETIC = 3, ORC_G_POSEIDON = 4 };
 #define ORC_UNUSED_SELECTOR 0xFFFFFFFFULL
 
-struct OrcGateInfo { int kind, selector_index, group_start, group_end; };
+struct OrcGateInfo { int kind, selector_index, group_start, group_end; int p[4]; };
+struct OpsBase;
+template <class O, class Emit> void orc_eval_gate(int kind, const int p[4], const typename O::T *w, const typename O::T *c, const u64 pi_hash[4], Emit emit);
 
 struct OrcCircuit {
     int degree_bits = 0, num_wires = 135, num_routed = 80, num_gate_constants = 2, num_selectors = 0;
@@ -31,14 +34,7 @@ struct OrcCircuit {
     int num_partial_products() const { return (num_routed + quotient_degree_factor - 1) / quotient_degree_factor - 1; }
     int num_zs_pp() const { return num_challenges * (1 + num_partial_products()); }
     int num_quotient_polys() const { return num_challenges * quotient_degree_factor; }
-    int num_gate_constraints() const {
-        int m = 0;
-        for (const OrcGateInfo &g : gates) {
-            int c = g.kind == ORC_G_CONSTANT ? 2 : g.kind == ORC_G_PUBLIC_INPUT ? 4 : g.kind == ORC_G_ARITHMETIC ? 20 : g.kind == ORC_G_POSEIDON ? 123 : 0;
-            if (c > m) m = c;
-        }
-        return m;
-    }
+    int num_gate_constraints() const;   /* max over the gates (counted by running each evaluator once) */
 };
 
 /* ---- field-generic helpers: T = u64 (base, canonical) or gl2 ---- */
@@ -86,13 +82,14 @@ template <class O> typename O::T orc_psd_sbox(typename O::T x) {
 /* Gate::eval_unfiltered.  `w` = local wires, `c` = local constants AFTER the selector prefix, emit(t) receives the
  * constraints in order. */
 template <class O, class Emit>
-void orc_eval_gate(int kind, const typename O::T *w, const typename O::T *c, const u64 pi_hash[4], Emit emit) {
+void orc_eval_gate(int kind, const int p[4], const typename O::T *w, const typename O::T *c, const u64 pi_hash[4], Emit emit) {
     typedef typename O::T T;
     if (kind == ORC_G_NOOP) return;
-    if (kind == ORC_G_CONSTANT) { for (int i = 0; i < 2; i++) emit(O::sub(c[i], w[i])); return; }
+    if (kind > ORC_G_POSEIDON) { orc_eval_gate_ext<O>(kind, p, w, c, emit); return; }
+    if (kind == ORC_G_CONSTANT) { for (int i = 0; i < p[0]; i++) emit(O::sub(c[i], w[i])); return; }
     if (kind == ORC_G_PUBLIC_INPUT) { for (int i = 0; i < 4; i++) emit(O::sub(w[i], O::from(pi_hash[i]))); return; }
     if (kind == ORC_G_ARITHMETIC) {
-        for (int i = 0; i < 20; i++) {
+        for (int i = 0; i < p[0]; i++) {
             T m0 = w[4 * i], m1 = w[4 * i + 1], ad = w[4 * i + 2], out = w[4 * i + 3];
             T computed = O::add(O::mul(O::mul(m0, m1), c[0]), O::mul(ad, c[1]));
             emit(O::sub(out, computed));
@@ -144,6 +141,18 @@ void orc_eval_gate(int kind, const typename O::T *w, const typename O::T *c, con
     for (int i = 0; i < 12; i++) emit(O::sub(st[i], w[12 + i]));
 }
 
+inline int OrcCircuit::num_gate_constraints() const {
+    int m = 0;
+    std::vector<u64> zeros(num_wires + 8, 0);
+    const u64 pi[4] = {0, 0, 0, 0};
+    for (const OrcGateInfo &g : gates) {
+        int k = 0;
+        orc_eval_gate<OpsBase>(g.kind, g.p, zeros.data(), zeros.data(), pi, [&](u64) { k++; });
+        if (k > m) m = k;
+    }
+    return m;
+}
+
 /* eval_vanishing_poly at one point for all challenges: terms = [L0(x)(Z-1)] ++ [partial-product checks] ++ [gate
  * constraints], reduced with powers of alpha.  consts = all local constants (selectors first), x = evaluation point
  * (the SHIFTED point in the prover).  z_h_x = Z_H(x), l0 = L_0(x). */
@@ -174,7 +183,7 @@ void orc_eval_vanishing(const OrcCircuit &C, typename O::T x, typename O::T l0, 
         const OrcGateInfo &g = C.gates[gi];
         T filter = orc_compute_filter<O>((int)gi, g.group_start, g.group_end, consts[g.selector_index], C.num_selectors > 1);
         int k = 0;
-        orc_eval_gate<O>(g.kind, w, consts + C.num_selectors, pi_hash, [&](T v) { gate_terms[k] = O::add(gate_terms[k], O::mul(filter, v)); k++; });
+        orc_eval_gate<O>(g.kind, g.p, w, consts + C.num_selectors, pi_hash, [&](T v) { gate_terms[k] = O::add(gate_terms[k], O::mul(filter, v)); k++; });
     }
     for (const T &t : gate_terms) terms.push_back(t);
     for (int ch = 0; ch < C.num_challenges; ch++) {   /* reduce_with_powers: term t gets alpha^t */

@@ -21,6 +21,7 @@ static double g_l3_maxabs = 0.0;   // largest lazy 96-bit magnitude built by ntt
 #include "../../eth-lc-plonky2_b200/csrc/ntt.cuh"
 #include "../../eth-lc-plonky2_b200/csrc/ntt_plan.h"
 #include "../../eth-lc-plonky2_b200/csrc/plonk.cuh"
+#include "../../eth-lc-plonky2_b200/csrc/gate_lib.h"
 
 static std::vector<std::unique_ptr<std::vector<u64>>> g_tables;
 
@@ -167,55 +168,121 @@ int emu_plan(u32 C, u32 log_n, u32 rate_bits, int intt, u64 *out, int max) {
     return k;
 }
 
-// ---- plonk rows: replay of quot_point / pp_row / pp_finish (kernel bodies) on host arrays ----
-static void emu_fill_circuit(const u64 *b, PlkCircuit &C) {
-    C.degree_bits = (u32)b[0]; C.num_wires = (u32)b[1]; C.num_routed = (u32)b[2]; C.num_gate_constants = (u32)b[3];
-    C.num_selectors = (u32)b[4]; C.num_challenges = (u32)b[5]; C.quotient_degree_factor = (u32)b[6]; C.num_gates = (u32)b[11];
-    for (u32 i = 0; i < C.num_gates; i++) {
-        C.gates[i].kind = (u32)b[12 + 4 * i]; C.gates[i].selector_index = (u32)b[13 + 4 * i];
-        C.gates[i].group_start = (u32)b[14 + 4 * i]; C.gates[i].group_end = (u32)b[15 + 4 * i];
+// ---- plonk rows: replay of the quotient kernels' bodies (quot_perm_point / quot_poseidon_point / quot_gates_point /
+// quot_finish_point, l0_table_group) and of pp_row / pp_finish on host arrays ----
+struct EmuCircuit {
+    u32 degree_bits, num_wires, num_routed, num_gate_constants, num_selectors, num_challenges, qdf, qdb, rate_bits;
+    std::vector<PlkGateDev> gates;
+    std::vector<u64> prog, imm;
+    u32 max_constraints = 0;
+    int poseidon_index = -1;
+};
+// both layouts of include/plonky2_b200.h; the programs are rebuilt from kinds + parameters with gate_lib.h unless the
+// description carries them
+static bool emu_parse_circuit(const u64 *b, EmuCircuit &C) {
+    const bool v2 = b[0] == 0x32424B4C50ull;
+    const u64 *h = v2 ? b + 2 : b;
+    C.degree_bits = (u32)h[0]; C.num_wires = (u32)h[1]; C.num_routed = (u32)h[2]; C.num_gate_constants = (u32)h[3];
+    C.num_selectors = (u32)h[4]; C.num_challenges = (u32)h[5]; C.qdf = (u32)h[6]; C.rate_bits = (u32)h[7];
+    C.qdb = 0;
+    while ((1u << C.qdb) < C.qdf) C.qdb++;
+    const u32 ng = (u32)h[11];
+    GvmImmPool pool;
+    const u64 *gt = v2 ? b + 20 : b + 12, *progs = gt + (size_t)ng * 12;
+    if (v2) {
+        const u64 *imms = progs + b[15];
+        for (u64 i = GVM_NUM_PI; i < b[14]; i++) { pool.values.push_back(gl_canon(imms[i])); pool.index.emplace(gl_canon(imms[i]), (u32)i); }
     }
+    for (u32 i = 0; i < ng; i++) {
+        const u64 *e = gt + (size_t)i * (v2 ? 12 : 4);
+        u32 p[4] = {0, 0, 0, 0};
+        const u32 kind = (u32)e[0];
+        if (v2) for (int k = 0; k < 4; k++) p[k] = (u32)e[4 + k];
+        else { if (kind == PLK_CONSTANT) p[0] = 2; if (kind == PLK_ARITHMETIC) p[0] = 20; }
+        std::vector<u64> program;
+        if (v2 && e[10]) program.assign(progs + e[9], progs + e[9] + e[10]);
+        else if (kind != PLK_NOOP) {
+            GvmBuilder B(pool);
+            if (!plk_build_gate(B, kind, p, C.num_wires, C.num_routed, C.num_gate_constants)) return false;
+            program = B.finish();
+            if (!B.ok) return false;
+        }
+        PlkGateDev g;
+        memset(&g, 0, sizeof(g));
+        g.prog_off = (u32)C.prog.size(); g.prog_len = (u32)program.size();
+        g.selector_index = (u32)e[1]; g.group_start = (u32)e[2]; g.group_end = (u32)e[3]; g.row = i;
+        C.prog.insert(C.prog.end(), program.begin(), program.end());
+        C.gates.push_back(g);
+        if (kind == PLK_POSEIDON && C.poseidon_index < 0) C.poseidon_index = (int)i;
+    }
+    C.imm = pool.values;
+    for (PlkGateDev &g : C.gates) {
+        u32 nc = 0;
+        if (g.prog_len && !gvm_validate(C.prog.data() + g.prog_off, g.prog_len, C.num_wires, C.num_gate_constants, (u32)C.imm.size(), &nc, nullptr)) return false;
+        g.num_constraints = nc;
+        if (nc > C.max_constraints) C.max_constraints = nc;
+    }
+    return true;
 }
-// LDEs are [cols][L] column-major in bit-reversed row order (the engine's layout); out: [num_challenges][L] natural order
-void emu_quotient_values(const u64 *blob, const u64 *cs_lde, const u64 *wires_lde, const u64 *zs_lde, const u64 *pi_hash,
-                         const u64 *betas, const u64 *gammas, const u64 *alphas, u64 *out) {
+// LDEs are [cols][L] column-major in bit-reversed row order (the engine's layout); out: [num_challenges][Lq] natural order.
+// native != 0: PoseidonGate through the FP64 evaluator (the default of the engine), otherwise through its bytecode.
+int emu_quotient_values(const u64 *blob, const u64 *cs_lde, const u64 *wires_lde, const u64 *zs_lde, const u64 *pi_hash,
+                        const u64 *betas, const u64 *gammas, const u64 *alphas, u64 *out, int native) {
     NttTableStore ts = make_store();
-    static bool pf_built = false;   // the FP64 PoseidonGate evaluator (PLK_POSEIDON_F64) reads the host tables
+    static bool pf_built = false;   // the FP64 PoseidonGate evaluator reads the host tables
     if (!pf_built) { psd_f64_build_tables(h_pf); pf_built = true; }
+    EmuCircuit C;
+    if (!emu_parse_circuit(blob, C)) return 1;
+    const u32 log_lq = C.degree_bits + C.qdb, nch = C.num_challenges;
+    const u64 n = (u64)1 << C.degree_bits, Lq = (u64)1 << log_lq, L = n << C.rate_bits;
+    const u32 npp = (C.num_routed + C.qdf - 1) / C.qdf - 1, perm_terms = nch + nch * (npp + 1);
     QuotParams q;
     memset(&q, 0, sizeof(q));
-    emu_fill_circuit(blob, q.C);
-    q.log_l = q.C.degree_bits + 3;
-    const u64 n = (u64)1 << q.C.degree_bits, L = n << 3;
+    q.log_n = C.degree_bits; q.log_lq = log_lq;
+    q.num_wires = C.num_wires; q.num_routed = C.num_routed; q.num_selectors = C.num_selectors; q.num_gate_constants = C.num_gate_constants;
+    q.num_challenges = nch; q.degree = C.qdf; q.npp = npp; q.stride = L;
     q.cs = cs_lde; q.wires = wires_lde; q.zs = zs_lde; q.out = out;
     q.k_is[0] = 1;
-    for (int j = 1; j < 80; j++) q.k_is[j] = h_gl_mul(q.k_is[j - 1], 7);
-    for (u32 i = 0; i < q.C.num_challenges; i++) { q.beta[i] = betas[i]; q.gamma[i] = gammas[i]; q.alpha[i] = alphas[i]; }
-    std::vector<u64> apow_tab((size_t)PLK_MAX_CHALLENGES * PLK_APOW_MAX);
-    plk_fill_apow(q.alpha, q.C.num_challenges, apow_tab.data());
-    q.apow = apow_tab.data();
-    for (int i = 0; i < 4; i++) q.pi_hash[i] = pi_hash[i];
-    const u64 g_pow_n = h_gl_pow(7, n), w8 = h_gl_root_of_unity(3);
-    for (int i = 0; i < 8; i++) { q.zh[i] = gl_canon(gl_sub(h_gl_mul(g_pow_n, h_gl_pow(w8, i)), 1)); q.zh_inv[i] = h_gl_inv(q.zh[i]); }
-    q.n_field = n % GL_P;
-    auto w = ts.w2((int)q.log_l, false);
-    q.w_lo = w.lo; q.w_hi = w.hi; q.w_lo_bits = w.lo_bits;
-    for (u64 pos = 0; pos < L; pos++) quot_point(q, pos);
+    for (int j = 1; j < PLK_MAX_ROUTED; j++) q.k_is[j] = h_gl_mul(q.k_is[j - 1], 7);
+    u64 alpha_c[PLK_MAX_CHALLENGES] = {0, 0};
+    for (u32 i = 0; i < nch; i++) { q.beta[i] = betas[i]; q.gamma[i] = gammas[i]; alpha_c[i] = alphas[i]; }
+    q.apow_stride = perm_terms + C.max_constraints + 1; q.first_gate_term = perm_terms;
+    std::vector<u64> apow_tab((size_t)PLK_MAX_CHALLENGES * q.apow_stride), acc((size_t)nch * Lq), l0(Lq);
+    plk_fill_apow(alpha_c, nch, q.apow_stride, apow_tab.data());
+    q.apow = apow_tab.data(); q.acc = acc.data(); q.l0 = l0.data();
+    for (int i = 0; i < 4; i++) C.imm[i] = gl_canon(pi_hash[i]);
+    const bool nat = native && C.poseidon_index >= 0;
+    for (size_t i = 0; i < C.gates.size(); i++) C.gates[i].native = nat && (int)i == C.poseidon_index;
+    q.gates = C.gates.data(); q.num_gates = (u32)C.gates.size(); q.prog = C.prog.data(); q.imm = C.imm.data();
+    q.has_poseidon = nat;
+    if (C.poseidon_index >= 0) q.poseidon = C.gates[C.poseidon_index];
+    L0Params lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.log_n = C.degree_bits; lp.log_lq = log_lq; lp.n_field = n % GL_P; lp.out = l0.data();
+    const u64 g_pow_n = h_gl_pow(7, n), wq = h_gl_root_of_unity((int)C.qdb);
+    for (u32 i = 0; i < (1u << C.qdb); i++) { lp.zh[i] = gl_canon(gl_sub(h_gl_mul(g_pow_n, h_gl_pow(wq, i)), 1)); q.zh_inv[i] = h_gl_inv(lp.zh[i]); }
+    auto w = ts.w2((int)log_lq, false);
+    q.w_lo = lp.w_lo = w.lo; q.w_hi = lp.w_hi = w.hi; q.w_lo_bits = lp.w_lo_bits = w.lo_bits;
+    for (u64 grp = 0; grp * L0_BATCH < Lq; grp++) l0_table_group(lp, grp);
+    for (u64 pos = 0; pos < Lq; pos++) quot_perm_point(q, pos);
+    if (nat) for (u64 pos = 0; pos < Lq; pos++) quot_poseidon_point(q, pos);
+    for (u64 pos = 0; pos < Lq; pos++) quot_gates_point(q, pos, !nat);
+    for (u64 pos = 0; pos < Lq; pos++) quot_finish_point(q, pos);
     g_tables.clear();
+    return 0;
 }
 void emu_partial_products(const u64 *blob, const u64 *wires, const u64 *sigmas, const u64 *betas, const u64 *gammas, u64 *out) {
     NttTableStore ts = make_store();
-    PlkCircuit C;
-    memset(&C, 0, sizeof(C));
-    emu_fill_circuit(blob, C);
+    EmuCircuit C;
+    if (!emu_parse_circuit(blob, C)) abort();
     PpParams p;
     memset(&p, 0, sizeof(p));
-    p.log_n = C.degree_bits; p.num_routed = C.num_routed; p.num_challenges = C.num_challenges; p.degree = C.quotient_degree_factor;
+    p.log_n = C.degree_bits; p.num_routed = C.num_routed; p.num_challenges = C.num_challenges; p.degree = C.qdf;
     const u64 n = (u64)1 << C.degree_bits;
     std::vector<u64> row_prod((size_t)C.num_challenges * n);
     p.wires = wires; p.sigmas = sigmas; p.out = out; p.row_prod = row_prod.data();
     p.k_is[0] = 1;
-    for (int j = 1; j < 80; j++) p.k_is[j] = h_gl_mul(p.k_is[j - 1], 7);
+    for (int j = 1; j < PLK_MAX_ROUTED; j++) p.k_is[j] = h_gl_mul(p.k_is[j - 1], 7);
     for (u32 i = 0; i < C.num_challenges; i++) { p.beta[i] = betas[i]; p.gamma[i] = gammas[i]; }
     auto w = ts.w2((int)C.degree_bits, false);
     p.w_lo = w.lo; p.w_hi = w.hi; p.w_lo_bits = w.lo_bits;

@@ -54,29 +54,8 @@ def test_partial_products_replay(emu, oracle, synth, db):
     assert (ref[0:2, 0] == 1).all()
 
 
-@pytest.fixture(scope="module")
-def emu_int_gate():
-    """The replay harness built with -DPLK_POSEIDON_F64=0: the PoseidonGate evaluator on the integer pipes ("fast" partial
-    rounds), kept as the A/B baseline of the default FP64 evaluator."""
-    import os
-    import subprocess
-    here = os.path.dirname(os.path.abspath(__file__))
-    src = os.path.join(here, "emu", "emu.cpp")
-    so = os.path.join(here, "emu", "libemu_intgate.so")
-    csrc = os.path.join(here, "..", "eth-lc-plonky2_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DPLK_POSEIDON_F64=0", "-o", so, src])
-    return C.CDLL(so)
-
-
-@pytest.mark.parametrize("variant", ["default", "int_gate"])
-@pytest.mark.parametrize("db", [3, 5])
-def test_quotient_point_replay(emu, emu_int_gate, oracle, synth, db, variant):
-    if variant == "int_gate":
-        emu = emu_int_gate
-    emu.emu_quotient_values.argtypes = [u64p] * 9
-    s = synth[db]
+def _quotient_replay(emu, oracle, s, db, native):
+    emu.emu_quotient_values.argtypes = [u64p] * 9 + [C.c_int]
     circ = oracle.Circuit(s["blob"])
     rng = np.random.default_rng(50 + db)
     betas, gammas, alphas = rand_field(rng, 2), rand_field(rng, 2), rand_field(rng, 2)
@@ -87,11 +66,62 @@ def test_quotient_point_replay(emu, emu_int_gate, oracle, synth, db, variant):
     L = 8 << db
     vals = np.zeros((2, L), np.uint64)
     lde = lambda b: np.ascontiguousarray(b.leaves.T)                               # engine layout: [cols][L] bit-reversed rows
-    emu.emu_quotient_values(s["blob"], lde(cs), lde(wires), lde(zs), s["pi_hash"], betas, gammas, alphas, vals)
+    assert emu.emu_quotient_values(s["blob"], lde(cs), lde(wires), lde(zs), s["pi_hash"], betas, gammas, alphas, vals, native) == 0
     # coset_ifft(7) of the replayed values must give the oracle's coefficients
+    inv7 = oracle.lib().orc_gl_inv(7)
+    pw = np.array([pow(inv7, k, oracle.P) for k in range(L)], dtype=object)
     for c in range(2):
         co = oracle.ifft(vals[c])
-        inv7 = oracle.lib().orc_gl_inv(7)
-        pw = np.array([pow(inv7, k, oracle.P) for k in range(L)], dtype=object)
         co = np.array([(int(a) * int(b)) % oracle.P for a, b in zip(co, pw)], dtype=np.uint64)
         assert (co.reshape(8, -1) == ref[8 * c:8 * c + 8]).all()
+
+
+@pytest.mark.parametrize("native", [1, 0], ids=["poseidon_fp64", "poseidon_bytecode"])
+@pytest.mark.parametrize("db", [3, 5])
+def test_quotient_point_replay(emu, oracle, synth, db, native):
+    """The four quotient kernels' bodies (PoseidonGate through the FP64 evaluator or through its bytecode; the other gates
+    through the interpreter) against the oracle's formulas."""
+    _quotient_replay(emu, oracle, synth[db], db, native)
+
+
+@pytest.fixture(scope="module")
+def synth_v2():
+    import eth_lc_plonky2_b200 as E
+    return {db: E.synth_circuit_v2(db, seed=5 + db) for db in (5, 6)}
+
+
+@pytest.mark.parametrize("db", [5, 6])
+def test_all_gate_kinds_oracle_prove_then_verify(oracle, synth_v2, db):
+    """Every gate of gate_lib.h in one circuit: the oracle evaluates them from its own formulas (oracle/gates.h)."""
+    s = synth_v2[db]
+    circ = oracle.Circuit(s["blob"])
+    cs = oracle.Batch.from_values(np.concatenate([s["constants"], s["sigmas"]]), 3, 4)
+    proof = circ.prove(cs, s["wires"], s["sigmas"], s["pi_hash"])
+    assert circ.verify(cs.cap, s["pi_hash"], proof) == 0
+
+
+@pytest.mark.parametrize("native", [1, 0], ids=["poseidon_fp64", "poseidon_bytecode"])
+def test_all_gate_kinds_quotient_replay(emu, oracle, synth_v2, native):
+    """Bytecode (gate_lib.h) vs formulas (oracle/gates.h) for all 18 gate kinds, through the quotient kernels' bodies."""
+    _quotient_replay(emu, oracle, synth_v2[5], 5, native)
+
+
+def test_every_gate_kind_is_violated_by_a_wrong_wire(oracle, synth_v2):
+    """Per gate kind: flipping one constrained wire of a row of that gate makes the oracle's verifier reject (the
+    constraints are not vacuous)."""
+    import eth_lc_plonky2_b200 as E
+    s = synth_v2[5]
+    b = [int(x) for x in s["blob"]]
+    ng = b[2 + 11]
+    kinds = [b[20 + 12 * i] for i in range(ng)]
+    circ = oracle.Circuit(s["blob"])
+    cs = oracle.Batch.from_values(np.concatenate([s["constants"], s["sigmas"]]), 3, 4)
+    nsel = b[2 + 4]
+    for gi, kind in enumerate(kinds):
+        if E.GATE_KINDS[kind] == "Noop":
+            continue
+        rows = np.where((s["constants"][:nsel] == gi).any(axis=0))[0]
+        assert len(rows), "gate %s has no row" % E.GATE_KINDS[kind]
+        bad = s["wires"].copy()
+        bad[0, int(rows[0])] ^= np.uint64(1)        # wire 0 is constrained in every gate of the library
+        assert circ.verify(cs.cap, s["pi_hash"], circ.prove(cs, bad, s["sigmas"], s["pi_hash"])) != 0, E.GATE_KINDS[kind]
