@@ -238,6 +238,25 @@ def test_full_size_properties(engine, oracle):
     assert sha(b8.merkle_tree.leaves(L - 4096, 4096)) == sha(o.leaves[L - 4096:])
 
 
+def test_full_config1_matches_oracle(engine, oracle):
+    """BASELINE configs[1] in full -- 135 columns x 2^20 rows, rate_bits 3, cap_height 4 -- against the oracle: coefficients,
+    every LDE leaf, every digest and the cap (VERDICT r1 task 1a; about a minute and ~20 GB of host memory for the oracle)."""
+    C_, log_n, r, h = 135, 20, 3, 4
+    L = 1 << (log_n + r)
+    vals = oracle.splitmix_columns(C_, 1 << log_n)
+    b = engine.PolynomialBatch.from_values(list(vals), r, False, h)
+    o = oracle.Batch.from_values(vals, r, h)
+    del vals
+    assert (b.merkle_tree.cap == o.cap).all()
+    assert sha(b.merkle_tree.digests) == sha(o.digests)
+    assert sha(b.polynomials) == sha(o.coeffs)
+    step = 1 << 18
+    for first in range(0, L, step):                      # 32 slices of 2^18 leaves (283 MB each)
+        assert sha(b.merkle_tree.leaves(first, step)) == sha(o.leaves[first:first + step]), "leaves %d.." % first
+    for k in (0, 1, L // 2 + 12345, L - 1):
+        assert (b.merkle_tree.prove(k) == o.prove(k)).all()
+
+
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_row_sharded_path_emulated_on_one_gpu(engine, oracle, world):
     """The kernels of the multi-GPU commit (eng_lde_dev with row shards, eng_merkle_new_dev over a row shard), with the

@@ -64,3 +64,114 @@ def test_invalid_witness_gives_a_proof_that_does_not_verify(engine, oracle):
     proof, _ = circ.prove(bad, s["pi_hash"])
     oc = oracle.Circuit(s["blob"])
     assert oc.verify(circ.constants_sigmas.merkle_tree.cap, s["pi_hash"], proof) == 21
+
+
+# ---- gates as bytecode (row a6 for the real gate set), product verifier (f4), circuit cache (f2) ----
+@pytest.mark.parametrize("db", [5, 8, 11])
+def test_all_gate_kinds_prove_matches_oracle_and_verifies(engine, oracle, db):
+    """18 gate kinds (core, recursion, plonky2_crypto u32) in one circuit: the engine interprets the gates' bytecode, the
+    oracle evaluates its own formulas (oracle/gates.h); proofs identical word for word, both verifiers accept."""
+    E = engine
+    s = E.synth_circuit_v2(db, seed=200 + db)
+    circ = E.Circuit.build(s)
+    assert circ.info.num_gates == 18
+    proof, ms = circ.prove(s["wires"], s["pi_hash"])
+    oc = oracle.Circuit(s["blob"])
+    ocs = oracle.Batch.from_values(np.concatenate([s["constants"], s["sigmas"]]), 3, 4)
+    assert oc.verify(ocs.cap, s["pi_hash"], proof) == 0
+    circ.verify(s["pi_hash"], proof)
+    ref = oc.prove(ocs, s["wires"], s["sigmas"], s["pi_hash"])
+    assert proof.shape == ref.shape and (proof == ref).all()
+
+
+@pytest.mark.parametrize("which,db", [("v1", 7), ("v2", 7)])
+def test_native_poseidon_gate_equals_bytecode(engine, which, db):
+    """quot_poseidon_kernel (FP64 permutation) against the interpreter running PoseidonGate's bytecode."""
+    E = engine
+    s = E.synth_circuit(db, seed=5) if which == "v1" else E.synth_circuit_v2(db, seed=5)
+    circ = E.Circuit.build(s)
+    rng = np.random.default_rng(db)
+    betas, gammas, alphas = rand_field(rng, 2), rand_field(rng, 2), rand_field(rng, 2)
+    wires = E.PolynomialBatch.from_values(list(s["wires"]), 3, False, 4)
+    zs = E.PolynomialBatch.from_values(list(circ.partial_products(s["wires"], betas, gammas)), 3, False, 4)
+    try:
+        E.set_option("quot_native_poseidon", 1)
+        a = circ.quotient(wires, zs, s["pi_hash"], betas, gammas, alphas).polynomials
+        E.set_option("quot_native_poseidon", 0)
+        b = circ.quotient(wires, zs, s["pi_hash"], betas, gammas, alphas).polynomials
+    finally:
+        E.set_option("quot_native_poseidon", 1)
+    assert (a == b).all()
+    assert (a[:, -1] != 0).any()      # degree really reaches 8n - 1 chunks (the quotient is not trivially zero)
+
+
+def test_engine_verifier_and_bytes_on_gpu_proofs(engine, oracle):
+    E = engine
+    s = E.synth_circuit_v2(9, seed=77)
+    circ = E.Circuit.build(s)
+    proof, _ = circ.prove(s["wires"], s["pi_hash"])
+    circ.verify(s["pi_hash"], proof)
+    data = E.proof_to_bytes(s["blob"], proof, [5, 6])
+    back, pis = E.proof_from_bytes(s["blob"], data)
+    assert (back == proof).all() and list(pis) == [5, 6]
+    bad = proof.copy(); bad[200] ^= np.uint64(1)
+    with pytest.raises(E.EngineError):
+        circ.verify(s["pi_hash"], bad)
+    # an unsatisfied U32 gate constraint: proof is produced, both verifiers reject
+    b = [int(x) for x in s["blob"]]
+    kinds = [b[20 + 12 * i] for i in range(b[13])]
+    gi = kinds.index(E.GATE_KINDS.index("U32Arithmetic"))
+    row = int(np.where((s["constants"][:b[6]] == gi).any(axis=0))[0][0])
+    w = s["wires"].copy(); w[3, row] ^= np.uint64(1)          # output_low of op 0
+    badp, _ = circ.prove(w, s["pi_hash"])
+    with pytest.raises(E.EngineError, match="vanishing"):
+        circ.verify(s["pi_hash"], badp)
+    oc = oracle.Circuit(s["blob"])
+    assert oc.verify(circ.constants_sigmas.merkle_tree.cap, s["pi_hash"], badp) == 21
+
+
+def test_circuit_cache_round_trip(engine, tmp_path):
+    """eng_circuit_save / eng_circuit_load (f2): the reloaded prover data gives the same cap and the same proof."""
+    E = engine
+    s = E.synth_circuit_v2(8, seed=31)
+    circ = E.Circuit.build(s)
+    path = tmp_path / "circuit.plk"
+    circ.save(path)
+    again = E.Circuit.load(path)
+    assert (again.blob == circ.blob).all()
+    assert (again.constants_sigmas.merkle_tree.cap == circ.constants_sigmas.merkle_tree.cap).all()
+    p1, _ = circ.prove(s["wires"], s["pi_hash"])
+    p2, _ = again.prove(s["wires"], s["pi_hash"])
+    assert (p1 == p2).all()
+    again.verify(s["pi_hash"], p2)
+    raw = bytearray(path.read_bytes())                          # a corrupted coefficient: the rebuilt commitment must not reproduce the stored cap
+    blob_words = int(np.frombuffer(bytes(raw[16:24]), np.uint64)[0])
+    off = 24 + 8 * blob_words + 16 + 8 * 64 + 8 * 5             # a coefficient of the first constants polynomial
+    raw[off] ^= 1
+    (tmp_path / "bad.plk").write_bytes(bytes(raw))
+    with pytest.raises(E.EngineError, match="cap"):
+        E.Circuit.load(tmp_path / "bad.plk")
+
+
+def test_prove_2_16_matches_oracle(engine, oracle):
+    """proof parity at 2^16 rows (the oracle needs about a minute)."""
+    E = engine
+    s = E.synth_circuit(16, seed=116)
+    circ = E.Circuit.build(s)
+    proof, _ = circ.prove(s["wires"], s["pi_hash"])
+    circ.verify(s["pi_hash"], proof)
+    oc = oracle.Circuit(s["blob"])
+    ocs = oracle.Batch.from_values(np.concatenate([s["constants"], s["sigmas"]]), 3, 4)
+    ref = oc.prove(ocs, s["wires"], s["sigmas"], s["pi_hash"])
+    assert proof.shape == ref.shape and (proof == ref).all()
+
+
+def test_prove_2_18_verifies(engine, oracle):
+    """2^18 rows, all gate kinds: verified by the product verifier and by the oracle's (verification is cheap at any size)."""
+    E = engine
+    s = E.synth_circuit_v2(18, seed=118)
+    circ = E.Circuit.build(s)
+    proof, _ = circ.prove(s["wires"], s["pi_hash"])
+    circ.verify(s["pi_hash"], proof)
+    oc = oracle.Circuit(s["blob"])
+    assert oc.verify(circ.constants_sigmas.merkle_tree.cap, s["pi_hash"], proof) == 0

@@ -125,3 +125,87 @@ def test_every_gate_kind_is_violated_by_a_wrong_wire(oracle, synth_v2):
         bad = s["wires"].copy()
         bad[0, int(rows[0])] ^= np.uint64(1)        # wire 0 is constrained in every gate of the library
         assert circ.verify(cs.cap, s["pi_hash"], circ.prove(cs, bad, s["sigmas"], s["pi_hash"])) != 0, E.GATE_KINDS[kind]
+
+
+# ---- row f4 on CPU: the product's verifier and byte format are host code (no device), checked against the ORACLE's prover ----
+@pytest.mark.parametrize("which,db", [("v1", 5), ("v1", 7), ("v2", 5), ("v2", 6)])
+def test_engine_verifier_accepts_oracle_proofs_and_rejects_tampering(oracle, synth, synth_v2, which, db):
+    import eth_lc_plonky2_b200 as E
+    s = (synth if which == "v1" else synth_v2)[db]
+    circ = oracle.Circuit(s["blob"])
+    cs = oracle.Batch.from_values(np.concatenate([s["constants"], s["sigmas"]]), 3, 4)
+    proof = circ.prove(cs, s["wires"], s["sigmas"], s["pi_hash"])
+    E.verify(s["blob"], cs.cap, s["pi_hash"], proof)                          # two verifiers, one proof
+    assert circ.verify(cs.cap, s["pi_hash"], proof) == 0
+    rng = np.random.default_rng(db)
+    for k in rng.integers(0, proof.size, 24):                                  # any flipped word is caught (or unparsable)
+        bad = proof.copy(); bad[int(k)] ^= np.uint64(1)
+        with pytest.raises(E.EngineError):
+            E.verify(s["blob"], cs.cap, s["pi_hash"], bad)
+    pi2 = s["pi_hash"].copy(); pi2[3] ^= np.uint64(1)
+    with pytest.raises(E.EngineError, match="vanishing"):
+        E.verify(s["blob"], cs.cap, pi2, proof)
+    bad_cap = np.array(cs.cap).copy(); bad_cap[0, 0] ^= np.uint64(1)
+    with pytest.raises(E.EngineError, match="Merkle"):
+        E.verify(s["blob"], bad_cap, s["pi_hash"], proof)
+    # an unsatisfied constraint: the prover still emits a proof, both verifiers reject at the vanishing identity
+    row = int(np.where((s["constants"][:1] != 0xFFFFFFFF).any(axis=0))[0][1])
+    w = s["wires"].copy(); w[0, row] ^= np.uint64(1)
+    badp = circ.prove(cs, w, s["sigmas"], s["pi_hash"])
+    if circ.verify(cs.cap, s["pi_hash"], badp) != 0:
+        with pytest.raises(E.EngineError):
+            E.verify(s["blob"], cs.cap, s["pi_hash"], badp)
+
+
+@pytest.mark.parametrize("which,db", [("v1", 5), ("v2", 6)])
+def test_proof_bytes_round_trip(oracle, synth, synth_v2, which, db):
+    """ProofWithPublicInputs::to_bytes / from_bytes: the byte length follows from the circuit's shapes (8 bytes per field
+    element, one count byte per Merkle path), the round trip is the identity and the reparsed proof still verifies."""
+    import eth_lc_plonky2_b200 as E
+    s = (synth if which == "v1" else synth_v2)[db]
+    circ = oracle.Circuit(s["blob"])
+    cs = oracle.Batch.from_values(np.concatenate([s["constants"], s["sigmas"]]), 3, 4)
+    proof = circ.prove(cs, s["wires"], s["sigmas"], s["pi_hash"])
+    pis = [1, 2, 3, 0xFFFFFFFF00000000]
+    data = E.proof_to_bytes(s["blob"], proof, pis)
+    nconst = s["constants"].shape[0]
+    arity = oracle.fri_arity_bits(db)
+    L_bits = db + 3
+    words = 3 * 64 + 2 * (nconst + 80 + 135 + 2 + 2 + 18 + 16) + len(arity) * 64 + 2 * (1 << (db - 4 * len(arity))) + 1 + len(pis)
+    paths = 0
+    for _ in range(28):
+        words += (nconst + 80) + 135 + 20 + 16 + 4 * 4 * (L_bits - 4)
+        paths += 4
+        lb = L_bits
+        for a in arity:
+            lb -= a
+            words += 2 * 16 + 4 * max(lb - 4, 0)
+            paths += 1
+    assert len(data) == 8 * words + paths
+    back, pis2 = E.proof_from_bytes(s["blob"], data)
+    assert (back == proof).all() and list(pis2) == pis
+    E.verify(s["blob"], cs.cap, s["pi_hash"], back)
+    with pytest.raises(E.EngineError):
+        E.proof_from_bytes(s["blob"], data[:-3])
+    nc = bytearray(data); nc[0:8] = (0xFFFFFFFFFFFFFFFF).to_bytes(8, "little")   # a non-canonical element is refused
+    with pytest.raises(E.EngineError):
+        E.proof_from_bytes(s["blob"], bytes(nc))
+
+
+def test_circuit_descriptions_are_validated():
+    """Programs that arrive over the ABI are checked before they reach a kernel: wire / constant / immediate indices,
+    registers read before written, unknown opcodes, constraint counts."""
+    import eth_lc_plonky2_b200 as E
+    s = E.synth_circuit_v2(4, seed=3, kinds_mask=(1 << 3) | (1 << 5))
+    blob = s["blob"]
+    cap = np.zeros((16, 4), np.uint64)
+    ng = int(blob[2 + 11])
+    prog0 = 20 + 12 * ng
+    def rejected(b, pat):
+        with pytest.raises(E.EngineError, match=pat):
+            E.verify(b, cap, s["pi_hash"], np.zeros(8, np.uint64))
+    b = blob.copy(); b[prog0] = np.uint64(99); rejected(b, "unknown opcode|invalid program")
+    b = blob.copy(); b[prog0] = np.uint64(int(b[prog0]) | (0x1FFF << 20)); rejected(b, "invalid program")
+    b = blob.copy(); b[1] += np.uint64(1); rejected(b, "inconsistent")
+    b = blob.copy(); b[20 + 1] = np.uint64(77); rejected(b, "selector index")
+    rejected(blob, "does not parse")                                          # a well-formed circuit, a garbage proof
