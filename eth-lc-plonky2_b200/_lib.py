@@ -43,6 +43,7 @@ _SIGNATURES = {
     "eng_synchronize": [],
     "eng_launch_count": [_u64p],
     "eng_set_option": [C.c_char_p, C.c_int64],
+    "eng_reserve": [C.c_size_t],
     "eng_measure_int_peak": [C.POINTER(C.c_double)],
     "eng_poseidon_permute": [_vp, _vp, C.c_size_t],
     "eng_hash_n": [_vp, C.c_size_t, C.c_size_t, C.c_int32, _vp],
@@ -82,6 +83,13 @@ _SIGNATURES = {
     "eng_blob_free": [_u64p],
     "eng_circuit_new": [_vp, _vp, C.POINTER(_vp), C.POINTER(_vp)],
     "eng_circuit_free": [_vp],
+    "eng_circuit_new_sharded": [_vp, C.POINTER(_vp), C.POINTER(_vp)],
+    "eng_partial_products_dev": [_vp, C.POINTER(_vp), _vp, _vp, _vp],
+    "eng_quotient_values_shard_dev": [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp],
+    "eng_quotient_coeffs_from_shards_dev": [_vp, _vp, C.c_uint32, _vp],
+    "eng_eval_ext_dev": [_vp, C.c_uint32, C.c_uint32, _vp, _vp],
+    "eng_fri_combine_shard_dev": [_vp, C.POINTER(_vp), C.POINTER(C.c_uint32), C.c_uint32, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp],
+    "eng_fri_prove_from_layer_dev": [_vp, _vp, _vp, C.POINTER(_u64p), C.POINTER(C.c_size_t), _vp],
     "eng_circuit_info": [_vp, C.POINTER(CircuitInfo)],
     "eng_circuit_describe": [_vp, _vp, C.c_uint32, _vp, C.POINTER(_u64p), C.POINTER(C.c_size_t)],
     "eng_circuit_save": [_vp, _vp, C.c_char_p],
@@ -162,6 +170,11 @@ def set_stream(cuda_stream_handle):
 def set_option(name, value):
     """eng_set_option: A/B switches of the engine (see include/plonky2_b200.h)."""
     check(load().eng_set_option(name.encode(), int(value)))
+
+
+def reserve(num_bytes):
+    """eng_reserve: grow the device memory pool ahead of the first proof."""
+    check(lib().eng_reserve(int(num_bytes)))
 
 
 def release_cached():

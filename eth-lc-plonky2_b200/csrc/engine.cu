@@ -6,6 +6,7 @@
 // reached from /root/reference/eth-lc-plonky2/src/main.rs:227 (build) and :230 (prove).
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -79,7 +80,8 @@ struct Ctx {
     bool table_upload_failed = false;        // a twiddle / power table could not be placed on the device (reported by tables_ok)
     // eng_set_option
     int opt_native_poseidon = 1;             // quotient: PoseidonGate through the native FP64 evaluator (0: its bytecode)
-    int opt_lde_group_mb = 48;               // LDE: megabytes of one (column, coset) group kept between the two passes (L2 residency)
+    int opt_reserve = 1;                     // eng_circuit_new / eng_circuit_load grow the pool to one proof's footprint
+    int opt_lde_group_mb = 0;                // LDE: megabytes of one (column, coset) group kept between the two passes (L2 residency)
 };
 Ctx g;
 
@@ -186,6 +188,18 @@ __global__ void gather_rows_kernel(const u64 *data, u64 row_stride, u64 col_stri
 // cache hit.  Going through cudaMallocAsync / cudaFreeAsync each time let the pool split and coalesce its blocks
 // differently from call to call, and every so often a 9 GB request went back to the driver (measured: sporadic
 // 0.2 ... 1 s stages in a 0.25 s proof).  All engine work is ordered on g.stream, so reuse needs no extra events.
+// ENG_TRACE=1: host wall-clock of the slow first-call steps (pool growth, table uploads) on stderr
+bool trace_on() { static int v = -1; if (v < 0) { const char *e = getenv("ENG_TRACE"); v = (e && *e && *e != '0') ? 1 : 0; } return v == 1; }
+double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// trace_mark("label"): with ENG_TRACE set, waits for the device and prints the wall clock since the previous mark
+void trace_mark(const char *label) {
+    if (!trace_on()) return;
+    static double last = 0.0;
+    cudaDeviceSynchronize();
+    const double now = wall_ms();
+    fprintf(stderr, "[eng trace] %-44s +%9.1f ms\n", label, last == 0.0 ? 0.0 : now - last);
+    last = now;
+}
 void cache_flush() {
     for (auto &kv : g.free_blocks) cudaFreeAsync(kv.second, g.stream);
     g.free_blocks.clear();
@@ -203,7 +217,12 @@ eng_status dev_alloc(u64 **p, size_t elems) {
         g.live_blocks[*p] = bytes;
         return ENG_OK;
     }
+    const double t0 = trace_on() ? wall_ms() : 0.0;
     cudaError_t e = cudaMallocAsync((void **)p, bytes, g.stream);
+    if (trace_on() && bytes >= ((size_t)64 << 20)) {
+        cudaStreamSynchronize(g.stream);
+        fprintf(stderr, "[eng trace] pool miss: %.2f GB in %.1f ms\n", bytes / 1e9, wall_ms() - t0);
+    }
     if (e != cudaSuccess && !g.free_blocks.empty()) {   // give the cached blocks back and retry once
         cudaGetLastError();
         cache_flush();
@@ -440,6 +459,7 @@ eng_status make_batch(const uint64_t *const *cols_host, const u64 *src_dev, bool
         return st;
     }
     b->leaf_data = b->lde; b->row_stride = 1; b->col_stride = L;
+    trace_mark("make_batch: buffers allocated");
 
     auto bail = [&](eng_status s) { if (g.copy_stream) cudaStreamSynchronize(g.copy_stream); destroy_batch(b); return s; };
 #define STB(call) do { eng_status s__ = (call); if (s__ != ENG_OK) return bail(s__); } while (0)
@@ -479,17 +499,32 @@ eng_status make_batch(const uint64_t *const *cols_host, const u64 *src_dev, bool
     } else {
         const u64 *src = src_dev;
         CUB(cudaEventRecord(g.ev[1], g.stream));
+        // Column groups (option lde_group_mb): the two passes of a transform run group by group, so that what pass 1 wrote
+        // (the four-step intermediate, one LDE column = 8 * L bytes) is still in the 126 MB L2 when pass 2 reads it --
+        // the intermediate then makes no HBM round trip.  0: one launch per pass over the whole batch.
+        const u64 group_bytes = (u64)g.opt_lde_group_mb << 20;
+        const uint32_t cg_lde = group_bytes ? (uint32_t)std::min<u64>(C, std::max<u64>(1, group_bytes / (L * sizeof(u64)))) : C;
+        const uint32_t cg_intt = group_bytes ? (uint32_t)std::min<u64>(C, std::max<u64>(1, group_bytes / (n * sizeof(u64)))) : C;
         if (is_values) {
             // iNTT; the (not yet written) LDE buffer is the four-step scratch
-            if (!ntt_plan_intt(g.tables, src, n, b->lde, n, b->coeffs, n, C, log_n, plan)) return bail(fail(ENG_ERR_INVALID, "iNTT size unsupported"));
-            STB(launch_plan(plan));
+            for (uint32_t c0 = 0; c0 < C; c0 += cg_intt) {
+                const uint32_t cc = std::min(cg_intt, C - c0);
+                plan.clear();
+                if (!ntt_plan_intt(g.tables, src + (size_t)c0 * n, n, b->lde + (size_t)c0 * n, n, b->coeffs + (size_t)c0 * n, n, cc, log_n, plan))
+                    return bail(fail(ENG_ERR_INVALID, "iNTT size unsupported"));
+                STB(launch_plan(plan));
+            }
         } else if (src != b->coeffs) {
             CUB(cudaMemcpyAsync(b->coeffs, src, (size_t)C * n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
         }
         CUB(cudaEventRecord(g.ev[2], g.stream));
-        plan.clear();
-        if (!ntt_plan_lde(g.tables, b->coeffs, n, b->lde, C, log_n, rate_bits, 0, plan)) return bail(fail(ENG_ERR_INVALID, "LDE size unsupported"));
-        STB(launch_plan(plan));
+        for (uint32_t c0 = 0; c0 < C; c0 += cg_lde) {
+            const uint32_t cc = std::min(cg_lde, C - c0);
+            plan.clear();
+            if (!ntt_plan_lde(g.tables, b->coeffs + (size_t)c0 * n, n, b->lde + (size_t)c0 * L, cc, log_n, rate_bits, 0, plan))
+                return bail(fail(ENG_ERR_INVALID, "LDE size unsupported"));
+            STB(launch_plan(plan));
+        }
     }
     if (blinding) {
         u64 count = (u64)SALT_SIZE * L;
@@ -499,8 +534,10 @@ eng_status make_batch(const uint64_t *const *cols_host, const u64 *src_dev, bool
         g.launches++;
         CUB(cudaGetLastError());
     }
+    trace_mark("make_batch: copies + transforms done");
     STB(build_tree(b));
     STB(collect_times(b, is_values, true));
+    trace_mark("make_batch: tree done");
 #undef STB
 #undef CUB
     *out = b;
@@ -530,7 +567,10 @@ eng_status eng_init(int32_t device) {
         return fail(ENG_ERR_STATE, "no CUDA device: %s (this engine has no CPU path)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     }
     if (device < 0 || device >= count) return fail(ENG_ERR_INVALID, "device %d out of range [0, %d)", device, count);
+    const double t_init0 = trace_on() ? wall_ms() : 0.0;
     CU(cudaSetDevice(device));
+    CU(cudaFree(nullptr));   // forces context creation here (so that the trace attributes it)
+    if (trace_on()) fprintf(stderr, "[eng trace] eng_init: CUDA context %.1f ms\n", wall_ms() - t_init0);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     g.device = device;
@@ -558,6 +598,7 @@ eng_status eng_init(int32_t device) {
     };
     g.launches = 0;
     g.ready = true;
+    if (trace_on()) fprintf(stderr, "[eng trace] eng_init: total %.1f ms\n", wall_ms() - t_init0);
     return ENG_OK;
 }
 
@@ -612,6 +653,33 @@ eng_status eng_release_cached(void) {
     return ENG_OK;
 }
 
+// Grows the stream-ordered pool to hold `bytes` of free memory now (one driver call instead of one per buffer of the
+// first proof: the pool maps device memory at ~50 GB/s, which the first eng_prove of a process otherwise pays buffer
+// by buffer).  Clamped to what the device has free; failure to grow is not an error (the pool grows on demand).
+eng_status eng_reserve(size_t bytes) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, g.device));
+    uint64_t reserved = 0, used = 0;
+    CU(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
+    CU(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
+    const uint64_t idle = reserved > used ? reserved - used : 0;     // includes the engine's exact-size cache
+    if (bytes <= idle) return ENG_OK;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const size_t margin = (size_t)2 << 30;
+    size_t want = bytes - idle;
+    if (free_b <= margin) return ENG_OK;
+    if (want > free_b - margin) want = free_b - margin;
+    const double t0 = trace_on() ? wall_ms() : 0.0;
+    void *p = nullptr;
+    if (cudaMallocAsync(&p, want, g.stream) != cudaSuccess) { cudaGetLastError(); return ENG_OK; }
+    cudaFreeAsync(p, g.stream);
+    if (trace_on()) { cudaStreamSynchronize(g.stream); fprintf(stderr, "[eng trace] eng_reserve: pool grown by %.2f GB in %.1f ms\n", want / 1e9, wall_ms() - t0); }
+    return ENG_OK;
+}
+
 eng_status eng_synchronize(void) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     ST(check_ready());
@@ -623,6 +691,7 @@ eng_status eng_set_option(const char *name, int64_t value) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!name) return fail(ENG_ERR_INVALID, "NULL option name");
     if (!strcmp(name, "quot_native_poseidon")) { g.opt_native_poseidon = value != 0; return ENG_OK; }
+    if (!strcmp(name, "reserve_for_proof")) { g.opt_reserve = value != 0; return ENG_OK; }
     if (!strcmp(name, "lde_group_mb")) { g.opt_lde_group_mb = value < 0 ? 0 : (int)value; return ENG_OK; }
     return fail(ENG_ERR_INVALID, "unknown option '%s'", name);
 }

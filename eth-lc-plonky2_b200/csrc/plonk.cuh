@@ -208,9 +208,13 @@ GL_HD u64 plk_filter(u32 row, u32 gs, u32 ge, u64 s, bool many) {
 struct QuotParams {
     u32 log_n, log_lq;             // rows; quotient domain = 2^log_lq = n * 2^quotient_degree_bits points (<= LDE size)
     u32 num_wires, num_routed, num_selectors, num_gate_constants, num_challenges, degree, npp;   // degree = quotient_degree_factor
-    u64 stride;                    // elements between LDE columns (= LDE size L)
-    const u64 *cs, *wires, *zs;    // LDE of constants||sigmas, wires, Z||partial products: [cols][L], bit-reversed rows; the
+    u64 stride;                    // elements between LDE columns (= LDE size L; = count for a row shard)
+    const u64 *cs, *wires, *zs;    // LDE of constants||sigmas, wires, Z||partial products: [cols][stride], bit-reversed rows; the
                                    // quotient domain is the first 2^log_lq rows (natural LDE indices that are multiples of L / Lq)
+    // Row shard (multi-GPU prover): the kernels cover positions [pos0, pos0 + count) of the quotient domain; row t of the
+    // column arrays, of acc and (by_position) of out is position pos0 + t.  Single GPU: pos0 = 0, count = 2^log_lq.
+    u64 pos0, count;
+    u32 by_position;               // out[c * count + t] in position order instead of out[c * Lq + natural index]
     u64 k_is[PLK_MAX_ROUTED];
     u64 beta[PLK_MAX_CHALLENGES], gamma[PLK_MAX_CHALLENGES];
     const u64 *apow;               // plk_fill_apow(alpha): [PLK_MAX_CHALLENGES][apow_stride]
@@ -239,8 +243,9 @@ GL_HD u64 quot_natural_index(const QuotParams &p, u64 pos) {
 }
 
 // L_0(x)(Z - 1) and the partial-product checks: terms 0 .. first_gate_term of the alpha-sum.
-GL_HD void quot_perm_point(const QuotParams &p, u64 pos) {
+GL_HD void quot_perm_point(const QuotParams &p, u64 t) {
     const u64 Lq = (u64)1 << p.log_lq;
+    const u64 pos = p.pos0 + t;
     const u64 i = quot_natural_index(p, pos);
     const u64 i_next = (i + (Lq >> p.log_n)) & (Lq - 1);       // multiply x by w_n
     u64 pos_next;
@@ -255,7 +260,8 @@ GL_HD void quot_perm_point(const QuotParams &p, u64 pos) {
     }
     const u64 x = gl_mul(gl_mul(p.w_lo[i & ((1ull << p.w_lo_bits) - 1)], p.w_hi[i >> p.w_lo_bits]), 7);
     const u32 nc = p.num_selectors + p.num_gate_constants, nch = p.num_challenges, npp = p.npp;
-    PlkCols sig = {p.cs + (u64)nc * p.stride, p.stride, pos}, w = {p.wires, p.stride, pos}, zs = {p.zs, p.stride, pos}, zn = {p.zs, p.stride, pos_next};
+    // i + Lq / n keeps the low bits of i, i.e. the high bits of pos: pos_next lies in the same row shard (<= 2^qdb shards)
+    PlkCols sig = {p.cs + (u64)nc * p.stride, p.stride, t}, w = {p.wires, p.stride, t}, zs = {p.zs, p.stride, t}, zn = {p.zs, p.stride, pos_next - p.pos0};
     PlkAcc acc;
     for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
     acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = 0;
@@ -276,13 +282,12 @@ GL_HD void quot_perm_point(const QuotParams &p, u64 pos) {
             plk_emit(acc, gl_sub(gl_mul(prev, num), gl_mul(next, den)));
         }
     }
-    for (u32 c = 0; c < nch; c++) p.acc[(u64)c * Lq + pos] = acc.sum[c];
+    for (u32 c = 0; c < nch; c++) p.acc[(u64)c * p.count + t] = acc.sum[c];
 }
 
 // PoseidonGate, native: acc += filter * sum_t alpha^(first_gate_term + t) c_t
-GL_HD void quot_poseidon_point(const QuotParams &p, u64 pos) {
-    const u64 Lq = (u64)1 << p.log_lq;
-    PlkCols cs = {p.cs, p.stride, pos}, w = {p.wires, p.stride, pos};
+GL_HD void quot_poseidon_point(const QuotParams &p, u64 t) {
+    PlkCols cs = {p.cs, p.stride, t}, w = {p.wires, p.stride, t};
     const PlkGateDev &g = p.poseidon;
     const u64 filter = plk_filter(g.row, g.group_start, g.group_end, cs[g.selector_index], p.num_selectors > 1);
     PlkAcc acc;
@@ -290,7 +295,7 @@ GL_HD void quot_poseidon_point(const QuotParams &p, u64 pos) {
     acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = p.first_gate_term;
     plk_poseidon_gate_f64(w, acc);
     for (u32 c = 0; c < p.num_challenges; c++) {
-        u64 *a = &p.acc[(u64)c * Lq + pos];
+        u64 *a = &p.acc[(u64)c * p.count + t];
         *a = gl_mul_add(filter, acc.sum[c], *a);
     }
 }
@@ -308,10 +313,9 @@ struct QuotGvmEmit {
     PlkAcc *acc;
     GL_HD void operator()(u64 v) { plk_emit(*acc, v); }
 };
-GL_HD void quot_gates_point(const QuotParams &p, u64 pos, bool include_native) {
-    const u64 Lq = (u64)1 << p.log_lq;
-    PlkCols cs = {p.cs, p.stride, pos};
-    QuotGvmCtx cx = {{p.wires, p.stride, pos}, {p.cs + (u64)p.num_selectors * p.stride, p.stride, pos}, p.imm};
+GL_HD void quot_gates_point(const QuotParams &p, u64 t, bool include_native) {
+    PlkCols cs = {p.cs, p.stride, t};
+    QuotGvmCtx cx = {{p.wires, p.stride, t}, {p.cs + (u64)p.num_selectors * p.stride, p.stride, t}, p.imm};
     u64 regs[GVM_NREG];
     u64 total[PLK_MAX_CHALLENGES] = {0, 0};
     for (u32 gi = 0; gi < p.num_gates; gi++) {
@@ -327,17 +331,33 @@ GL_HD void quot_gates_point(const QuotParams &p, u64 pos, bool include_native) {
         for (int c = 0; c < PLK_MAX_CHALLENGES; c++) total[c] = gl_mul_add(filter, acc.sum[c], total[c]);
     }
     for (u32 c = 0; c < p.num_challenges; c++) {
-        u64 *a = &p.acc[(u64)c * Lq + pos];
+        u64 *a = &p.acc[(u64)c * p.count + t];
         *a = gl_add(*a, total[c]);
     }
 }
 
 // * 1 / Z_H(x); position -> natural index
-GL_HD void quot_finish_point(const QuotParams &p, u64 pos) {
+GL_HD void quot_finish_point(const QuotParams &p, u64 t) {
     const u64 Lq = (u64)1 << p.log_lq;
-    const u64 i = quot_natural_index(p, pos);
+    const u64 i = quot_natural_index(p, p.pos0 + t);
     const u64 zi = p.zh_inv[i & ((Lq >> p.log_n) - 1)];
-    for (u32 c = 0; c < p.num_challenges; c++) p.out[(u64)c * Lq + i] = gl_canon(gl_mul(p.acc[(u64)c * Lq + pos], zi));
+    for (u32 c = 0; c < p.num_challenges; c++) {
+        const u64 v = gl_canon(gl_mul(p.acc[(u64)c * p.count + t], zi));
+        if (p.by_position) p.out[(u64)c * p.count + t] = v;
+        else p.out[(u64)c * Lq + i] = v;
+    }
+}
+// gathered row shards [G][num_challenges][Lq / G] in position order -> [num_challenges][Lq] in natural order
+GL_HD void quot_unshard_point(const u64 *in, u64 *out, u32 log_lq, u32 log_shards, u32 nch, u64 pos) {
+    const u64 Lq = (u64)1 << log_lq, count = Lq >> log_shards;
+    const u64 g = pos / count, t = pos % count;
+    u64 i = 0;
+#ifdef __CUDA_ARCH__
+    i = log_lq ? (__brevll(pos) >> (64 - log_lq)) : 0;
+#else
+    for (u32 b = 0; b < log_lq; b++) i |= ((pos >> b) & 1) << (log_lq - 1 - b);
+#endif
+    for (u32 c = 0; c < nch; c++) out[(u64)c * Lq + i] = in[(g * nch + c) * count + t];
 }
 
 // L_0 table: l0[pos] = zh[i mod 2^qdb] / (n (x_i - 1)), x_i = 7 w_Lq^i, i = bitrev(pos); 8 positions per thread share one
@@ -441,24 +461,29 @@ GL_HD void pp_finish(const PpParams &p, u64 i) {
 
 #ifdef __CUDACC__
 __global__ void __launch_bounds__(128) quot_perm_kernel(QuotParams p) {
-    const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >> p.log_lq) return;
-    quot_perm_point(p, pos);
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.count) return;
+    quot_perm_point(p, t);
 }
 __global__ void __launch_bounds__(128) quot_poseidon_kernel(QuotParams p) {
-    const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >> p.log_lq) return;
-    quot_poseidon_point(p, pos);
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.count) return;
+    quot_poseidon_point(p, t);
 }
 __global__ void __launch_bounds__(128) quot_gates_kernel(QuotParams p, int include_native) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.count) return;
+    quot_gates_point(p, t, include_native != 0);
+}
+__global__ void __launch_bounds__(256) quot_unshard_kernel(const u64 *in, u64 *out, u32 log_lq, u32 log_shards, u32 nch) {
     const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >> p.log_lq) return;
-    quot_gates_point(p, pos, include_native != 0);
+    if (pos >> log_lq) return;
+    quot_unshard_point(in, out, log_lq, log_shards, nch, pos);
 }
 __global__ void __launch_bounds__(256) quot_finish_kernel(QuotParams p) {
-    const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >> p.log_lq) return;
-    quot_finish_point(p, pos);
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.count) return;
+    quot_finish_point(p, t);
 }
 __global__ void __launch_bounds__(128) l0_table_kernel(L0Params p) {
     const u64 grp = (u64)blockIdx.x * blockDim.x + threadIdx.x;

@@ -129,19 +129,21 @@ struct FriCombineParams {
     gl2 shift[FRI_MAX_BATCHES];       // alpha^(size of batch i): final = final * shift[i] + quotient_i
     const u64 *w_lo, *w_hi;           // two-level powers of w_L
     u32 w_lo_bits;
-    u64 *out;                         // layer 0: [L][2], position p <-> x = 7 * w_L^{bitrev(p)}
+    u64 *out;                         // layer 0: [count][2], entry t <-> position p = pos0 + t <-> x = 7 * w_L^{bitrev(p)}
+    u64 pos0, count;                  // row shard of the multi-GPU prover (single GPU: 0, L); cols[k] is indexed by p - pos0
 };
 #ifdef __CUDACC__
 __global__ void __launch_bounds__(256) fri_combine_kernel(FriCombineParams p) {
-    const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >> p.log_l) return;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.count) return;
+    const u64 pos = p.pos0 + t;
     const u64 j = __brevll(pos) >> (64 - p.log_l);
     const u64 x = gl_mul(gl_mul(p.w_lo[j & ((1ull << p.w_lo_bits) - 1)], p.w_hi[j >> p.w_lo_bits]), 7);
     gl2 fin = gl2_make(0, 0);
     for (u32 b = 0; b < p.num_batches; b++) {
         u64 aa = 0, ab = 0;  // sum alpha^j f_j(x): accumulate the two coordinates separately
         for (u32 k = p.first[b]; k < p.first[b + 1]; k++) {
-            u64 v = p.cols[k][pos];
+            u64 v = p.cols[k][t];
             gl2 a = p.alpha_pow[k - p.first[b]];
             aa = gl_mul_add(a.a, v, aa);
             ab = gl_mul_add(a.b, v, ab);
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256) fri_combine_kernel(FriCombineParams p) {
         fin = gl2_add(gl2_mul(fin, p.shift[b]), q);
     }
     fin = gl2_canon(fin);
-    reinterpret_cast<ulonglong2 *>(p.out)[pos] = make_ulonglong2(fin.a, fin.b);
+    reinterpret_cast<ulonglong2 *>(p.out)[t] = make_ulonglong2(fin.a, fin.b);
 }
 
 // One thread per Merkle leaf (16 extension values e_i at x0 * w_16^{bitrev4(i)}): a_t = (1/16) sum_m w_16^{-mt} E_m with

@@ -47,11 +47,17 @@ eng_status eng_synchronize(void);
 /* Released device buffers are kept (by exact size) for the next call of the same shape; this returns them, and the
  * stream-ordered pool's unused memory, to the driver. */
 eng_status eng_release_cached(void);
+/* Grows the device memory pool so that `bytes` are free in it (cold start: the first proof of a process otherwise pays
+ * the pool's growth buffer by buffer).  eng_circuit_new / eng_circuit_load call it with the footprint of one eng_prove
+ * (option "reserve_for_proof", default 1); a prover can also call it early, while the host still builds the circuit. */
+eng_status eng_reserve(size_t bytes);
 eng_status eng_launch_count(uint64_t *out);       /* kernels launched by the engine since eng_init */
 /* Engine options (A/B switches used by tests and profiles; defaults are the product path):
  *   "quot_native_poseidon" 1  PoseidonGate through the native FP64 evaluator (0: through its bytecode, like every other gate)
- *   "lde_group_mb"         48 megabytes of LDE a (columns x cosets) group may hold between the two passes of the transform
- *                             so that the second pass reads it from L2 (0: one launch per pass over the whole batch) */
+ *   "lde_group_mb"         0  megabytes of four-step intermediate a column group may hold between the two passes of a
+ *                             transform so that the second pass reads it from the 126 MB L2 instead of HBM
+ *                             (0: one launch per pass over the whole batch; measured in profiles/r02_ntt.md)
+ *   "reserve_for_proof"    1  eng_circuit_new / eng_circuit_load grow the memory pool to one proof's footprint */
 eng_status eng_set_option(const char *name, int64_t value);
 
 /* Measured integer issue rates of this device, thread-operations per second:
@@ -252,6 +258,42 @@ eng_status eng_quotient(const eng_circuit *c, const eng_batch *wires, const eng_
  * commit, opening set, opening proofs (FRI), total. */
 eng_status eng_prove(const eng_circuit *c, const uint64_t *const *wire_cols_host, const uint64_t *public_inputs_hash,
                      uint64_t **blob_out, size_t *blob_len, float *stage_ms);
+
+/* ---- multi-GPU prover: prove_with_partition_witness over the GPUs of one box, one process per GPU ----
+ * Every committed batch (constants||sigmas, wires, Z||partial products, quotient chunks) is column-sharded for the
+ * iNTT / LDE and row-sharded for hashing (eng_lde_peer_dev / eng_merkle_new_dev); after the column -> row exchange rank g
+ * holds the leaf matrix [cols][L/G] of each batch.  The steps that read whole ROWS -- gate constraints + permutation checks
+ * of the quotient, the FRI combination -- run on those leaf matrices without further exchange:
+ *   x -> w_n x moves an LDE position inside its row shard as long as G <= 2^quotient_degree_bits, so Z(w_n x) is local;
+ *   16 consecutive positions (one FRI coset / Merkle leaf of the first commit-phase layer) never straddle row shards.
+ * Host orchestration (transcript, all-gathers of the quotient values / layer 0 / openings): eth-lc-plonky2_b200/parallel.py
+ * ShardedProver; the proof it assembles is bit-identical to eng_prove's.  Replaces the rayon parallelism inside
+ * plonky2::plonk::prover::prove_with_partition_witness (/root/reference/eth-lc-plonky2/src/main.rs:230). */
+eng_status eng_circuit_new_sharded(const uint64_t *blob, const uint64_t *const *sigma_cols_host, eng_circuit **out);
+/* a5 with the result left on the device: out_dev [num_challenges * (1 + num_partial_products)][n] */
+eng_status eng_partial_products_dev(const eng_circuit *c, const uint64_t *const *wire_cols_host, const uint64_t *betas,
+                                    const uint64_t *gammas, uint64_t *out_dev);
+/* a6 on row shard `shard` of 2^log_shards: quotient values at LDE positions [shard * L/G, (shard + 1) * L/G) from this rank's
+ * leaf matrices ([cols][L/G] column-major) -> out_dev [num_challenges][L/G], position order.  Needs quotient_degree_bits ==
+ * rate_bits and G <= 2^quotient_degree_bits. */
+eng_status eng_quotient_values_shard_dev(const eng_circuit *c, const uint64_t *cs_rows_dev, const uint64_t *wires_rows_dev,
+                                         const uint64_t *zs_rows_dev, uint32_t log_shards, uint32_t shard, const uint64_t *public_inputs_hash,
+                                         const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas, uint64_t *out_dev);
+/* gathered shards [G][num_challenges][L/G] -> natural order -> coset iNTT -> chunk coefficients [num_challenges * qdf][n] */
+eng_status eng_quotient_coeffs_from_shards_dev(const eng_circuit *c, const uint64_t *gathered_dev, uint32_t log_shards, uint64_t *coeffs_out_dev);
+/* a7 on a device coefficient array [num_polys][2^log_n] (a rank's column shard) -> out_host [num_polys][2] */
+eng_status eng_eval_ext_dev(const uint64_t *coeffs_dev, uint32_t num_polys, uint32_t log_n, const uint64_t z[2], uint64_t *out_host);
+/* a8, first half, on a row shard: FRI layer 0 (the combined, divided codeword) at positions [shard * L/G, ...).  instance:
+ * as for eng_fri_prove_openings; rows_dev[o] / widths[o]: leaf matrix and width of oracle o; openings_host: the claimed
+ * values (a, b) of every polynomial of the instance in instance order; alpha: drawn by the caller.  out_dev [L/G][2]. */
+eng_status eng_fri_combine_shard_dev(const uint64_t *instance, const uint64_t *const *rows_dev, const uint32_t *widths, uint32_t num_oracles,
+                                     const uint64_t *openings_host, const uint64_t alpha[2], uint32_t log_l, uint32_t log_shards,
+                                     uint32_t shard, uint64_t *out_dev);
+/* a8, second half, from the gathered layer 0 ([L][2], position order): commit phase, final polynomial, proof of work, query
+ * indices, commit-phase openings.  Blob = FriProof layout with 0 initial oracles per query round; the caller opens rows
+ * query_indices_out[0 .. num_query_rounds) of the initial oracles on the ranks that own them and splices them in. */
+eng_status eng_fri_prove_from_layer_dev(const uint64_t *layer0_dev, eng_challenger *ch, const int32_t *params, uint64_t **blob_out,
+                                        size_t *blob_len, uint64_t *query_indices_out);
 
 /* ---- f4: CircuitData::verify and ProofWithPublicInputs::{to_bytes, from_bytes}  [plonky2:plonk/verifier.rs,
  * util/serialization]; reached from /root/reference/eth-lc-plonky2/src/main.rs:233 ----

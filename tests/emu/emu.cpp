@@ -226,8 +226,16 @@ static bool emu_parse_circuit(const u64 *b, EmuCircuit &C) {
 }
 // LDEs are [cols][L] column-major in bit-reversed row order (the engine's layout); out: [num_challenges][Lq] natural order.
 // native != 0: PoseidonGate through the FP64 evaluator (the default of the engine), otherwise through its bytecode.
+int emu_quotient_values_sharded(const u64 *blob, const u64 *cs_lde, const u64 *wires_lde, const u64 *zs_lde, const u64 *pi_hash,
+                                const u64 *betas, const u64 *gammas, const u64 *alphas, u64 *out, int native, u32 log_shards);
 int emu_quotient_values(const u64 *blob, const u64 *cs_lde, const u64 *wires_lde, const u64 *zs_lde, const u64 *pi_hash,
                         const u64 *betas, const u64 *gammas, const u64 *alphas, u64 *out, int native) {
+    return emu_quotient_values_sharded(blob, cs_lde, wires_lde, zs_lde, pi_hash, betas, gammas, alphas, out, native, 0);
+}
+// log_shards > 0: the multi-GPU prover's path -- every row shard is cut out of the LDEs as its own [cols][L/G] leaf matrix,
+// evaluated with pos0 / count / by_position, and the gathered shards go through quot_unshard_point
+int emu_quotient_values_sharded(const u64 *blob, const u64 *cs_lde, const u64 *wires_lde, const u64 *zs_lde, const u64 *pi_hash,
+                                const u64 *betas, const u64 *gammas, const u64 *alphas, u64 *out, int native, u32 log_shards) {
     NttTableStore ts = make_store();
     static bool pf_built = false;   // the FP64 PoseidonGate evaluator reads the host tables
     if (!pf_built) { psd_f64_build_tables(h_pf); pf_built = true; }
@@ -240,7 +248,7 @@ int emu_quotient_values(const u64 *blob, const u64 *cs_lde, const u64 *wires_lde
     memset(&q, 0, sizeof(q));
     q.log_n = C.degree_bits; q.log_lq = log_lq;
     q.num_wires = C.num_wires; q.num_routed = C.num_routed; q.num_selectors = C.num_selectors; q.num_gate_constants = C.num_gate_constants;
-    q.num_challenges = nch; q.degree = C.qdf; q.npp = npp; q.stride = L;
+    q.num_challenges = nch; q.degree = C.qdf; q.npp = npp; q.stride = L; q.pos0 = 0; q.count = Lq;
     q.cs = cs_lde; q.wires = wires_lde; q.zs = zs_lde; q.out = out;
     q.k_is[0] = 1;
     for (int j = 1; j < PLK_MAX_ROUTED; j++) q.k_is[j] = h_gl_mul(q.k_is[j - 1], 7);
@@ -264,10 +272,35 @@ int emu_quotient_values(const u64 *blob, const u64 *cs_lde, const u64 *wires_lde
     auto w = ts.w2((int)log_lq, false);
     q.w_lo = lp.w_lo = w.lo; q.w_hi = lp.w_hi = w.hi; q.w_lo_bits = lp.w_lo_bits = w.lo_bits;
     for (u64 grp = 0; grp * L0_BATCH < Lq; grp++) l0_table_group(lp, grp);
-    for (u64 pos = 0; pos < Lq; pos++) quot_perm_point(q, pos);
-    if (nat) for (u64 pos = 0; pos < Lq; pos++) quot_poseidon_point(q, pos);
-    for (u64 pos = 0; pos < Lq; pos++) quot_gates_point(q, pos, !nat);
-    for (u64 pos = 0; pos < Lq; pos++) quot_finish_point(q, pos);
+    if (log_shards == 0) {
+        for (u64 pos = 0; pos < Lq; pos++) quot_perm_point(q, pos);
+        if (nat) for (u64 pos = 0; pos < Lq; pos++) quot_poseidon_point(q, pos);
+        for (u64 pos = 0; pos < Lq; pos++) quot_gates_point(q, pos, !nat);
+        for (u64 pos = 0; pos < Lq; pos++) quot_finish_point(q, pos);
+        g_tables.clear();
+        return 0;
+    }
+    if (Lq != L || log_shards > C.qdb) { g_tables.clear(); return 2; }
+    const u32 G = 1u << log_shards;
+    const u64 count = Lq >> log_shards;
+    const u32 ncs = C.num_selectors + C.num_gate_constants + C.num_routed, nzs = nch * (1 + npp);
+    std::vector<u64> gathered((size_t)nch * Lq);
+    for (u32 gsh = 0; gsh < G; gsh++) {
+        auto cut = [&](const u64 *lde, u32 cols) {
+            std::vector<u64> m((size_t)cols * count);
+            for (u32 c2 = 0; c2 < cols; c2++) memcpy(&m[(size_t)c2 * count], lde + (size_t)c2 * L + (size_t)gsh * count, count * 8);
+            return m;
+        };
+        std::vector<u64> mcs = cut(cs_lde, ncs), mw = cut(wires_lde, C.num_wires), mz = cut(zs_lde, nzs), sacc((size_t)nch * count);
+        QuotParams s2 = q;
+        s2.cs = mcs.data(); s2.wires = mw.data(); s2.zs = mz.data(); s2.stride = count; s2.pos0 = (u64)gsh * count; s2.count = count;
+        s2.by_position = 1; s2.acc = sacc.data(); s2.out = &gathered[(size_t)gsh * nch * count];
+        for (u64 t = 0; t < count; t++) quot_perm_point(s2, t);
+        if (nat) for (u64 t = 0; t < count; t++) quot_poseidon_point(s2, t);
+        for (u64 t = 0; t < count; t++) quot_gates_point(s2, t, !nat);
+        for (u64 t = 0; t < count; t++) quot_finish_point(s2, t);
+    }
+    for (u64 pos = 0; pos < Lq; pos++) quot_unshard_point(gathered.data(), out, log_lq, log_shards, nch, pos);
     g_tables.clear();
     return 0;
 }

@@ -84,6 +84,28 @@ def test_quotient_point_replay(emu, oracle, synth, db, native):
     _quotient_replay(emu, oracle, synth[db], db, native)
 
 
+@pytest.mark.parametrize("log_shards", [1, 2, 3])
+def test_row_sharded_quotient_replay(emu, oracle, synth, log_shards):
+    """The multi-GPU prover's quotient: every row shard evaluated from its own leaf matrices (pos0 / count / by_position),
+    gathered and un-sharded, equals the single-device values (Z(w_n x) stays inside a shard for up to 2^3 shards)."""
+    s = synth[5]
+    circ = oracle.Circuit(s["blob"])
+    rng = np.random.default_rng(77)
+    betas, gammas, alphas = rand_field(rng, 2), rand_field(rng, 2), rand_field(rng, 2)
+    cs = oracle.Batch.from_values(np.concatenate([s["constants"], s["sigmas"]]), 3, 4)
+    wires = oracle.Batch.from_values(s["wires"], 3, 4)
+    zs = oracle.Batch.from_values(circ.partial_products(s["wires"], s["sigmas"], betas, gammas), 3, 4)
+    lde = lambda b: np.ascontiguousarray(b.leaves.T)
+    L = 8 << 5
+    args = (s["blob"], lde(cs), lde(wires), lde(zs), s["pi_hash"], betas, gammas, alphas)
+    emu.emu_quotient_values_sharded.argtypes = [u64p] * 9 + [C.c_int, C.c_uint32]
+    one, many = np.zeros((2, L), np.uint64), np.zeros((2, L), np.uint64)
+    assert emu.emu_quotient_values_sharded(*args, one, 1, 0) == 0
+    assert emu.emu_quotient_values_sharded(*args, many, 1, log_shards) == 0
+    assert (one == many).all() and one.any()
+    assert emu.emu_quotient_values_sharded(*args, many, 1, 4) == 2       # 16 shards > 2^quotient_degree_bits: refused
+
+
 @pytest.fixture(scope="module")
 def synth_v2():
     import eth_lc_plonky2_b200 as E
