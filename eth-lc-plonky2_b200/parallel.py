@@ -333,3 +333,266 @@ class ShardedPolynomialBatch:
     def local_digests(self):
         """This rank's slice of the global `digests` vector (slices concatenate in rank order)."""
         return self.merkle_tree_local.digests
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Multi-GPU prover (SURVEY.md 8(e); include/plonky2_b200.h "multi-GPU prover")
+# ---------------------------------------------------------------------------------------------------------------------
+P = 0xFFFFFFFF00000001
+_POWER_OF_TWO_GENERATOR = 1753635133440165772
+_BLOB_V2_MAGIC = 0x32424B4C50
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def splice_initial_openings(fri_blob, openings):
+    """fri_blob: FriProof blob of eng_fri_prove_from_layer_dev (0 initial oracles per query round); openings[q] = [(leaf row,
+    siblings [layers][4]) per oracle] -> the blob eng_fri_prove_openings would have produced."""
+    b = [int(x) for x in fri_blob]
+    i = 0
+    r = b[i]; i += 1
+    for _ in range(r):
+        i += 1 + b[i]
+    f = b[i]; i += 1 + 2 * f
+    i += 1                                   # pow_witness
+    q = b[i]; i += 1
+    out = b[:i]
+    if q != len(openings):
+        raise EngineError(_lib.ENG_ERR_INVALID, "%d query rounds, openings for %d" % (q, len(openings)))
+    for k in range(q):
+        if b[i] != 0:
+            raise EngineError(_lib.ENG_ERR_INVALID, "query round %d already carries initial-tree openings" % k)
+        i += 1
+        out.append(len(openings[k]))
+        for leaf, path in openings[k]:
+            leaf, path = _u64(leaf).ravel(), _u64(path).reshape(-1, 4)
+            out += [leaf.size] + [int(x) for x in leaf] + [path.shape[0]] + [int(x) for x in path.ravel()]
+        s = b[i]; j = i + 1
+        for _ in range(s):
+            j += 1 + 2 * b[j]
+            j += 1 + 4 * b[j]
+        out += b[i:j]
+        i = j
+    if i != len(b):
+        raise EngineError(_lib.ENG_ERR_INVALID, "trailing words in the FRI blob")
+    return np.array(out, np.uint64)
+
+
+class ShardedProver:
+    """prove_with_partition_witness (after witness generation) over the `world` GPUs of one box, one process per GPU.
+
+    Every batch is committed column-sharded / row-sharded (ShardedPolynomialBatch); the quotient's constraint evaluation and
+    the FRI combination run on this rank's leaf matrices (x -> w_n x and the 16-point FRI cosets stay inside a row shard);
+    the cheap steps are replicated (transcript, partial products, the quotient's coset iNTT, the FRI commit phase on the
+    gathered layer 0).  Collectives: the fused column -> row exchange of four commitments, the cap all-gathers, one
+    all-gather of the quotient values (num_challenges * L * 8 B in total), one of FRI layer 0 (L * 16 B), two small object
+    gathers (openings at zeta, query openings).  The proof is bit-identical to eng_prove's on one GPU."""
+
+    STAGES = ("wires commitment", "partial products", "Z commitment", "quotient polys", "quotient commitment", "opening set",
+              "opening proofs (FRI)", "total")
+
+    def __init__(self, blob, constants, sigmas, rank, world, device=None, group=None, dist=None, use_peer=True, ops=None):
+        import torch
+        self.torch = torch
+        if dist is None:
+            import torch.distributed as dist
+        self.dist, self.group, self.rank, self.world = dist, group, rank, world
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.ops = ops if ops is not None else EngineOps(self.device)
+        self.blob = _u64(blob)
+        lib = _lib.lib()
+        sig = [_u64(c) for c in sigmas]
+        ptrs = (C.c_void_p * len(sig))(*[c.ctypes.data for c in sig])
+        self._h = C.c_void_p()
+        check(lib.eng_circuit_new_sharded(_ptr(self.blob), ptrs, C.byref(self._h)))
+        info = _lib.CircuitInfo()
+        check(lib.eng_circuit_info(self._h, C.byref(info)))
+        self.info = info
+        b = [int(x) for x in self.blob]
+        v2 = b[0] == _BLOB_V2_MAGIC
+        h = b[2:] if v2 else b
+        self.pow_bits, self.num_query_rounds, ng = h[9], h[10], h[11]
+        self.digest = np.array(b[16:20] if v2 else b[12 + 4 * ng:16 + 4 * ng], np.uint64)
+        self.log_world = _log2_strict(world, "world size")
+        qdb = (info.quotient_degree_factor - 1).bit_length()
+        if qdb != info.rate_bits or self.log_world > qdb:
+            raise EngineError(_lib.ENG_ERR_INVALID, "the sharded prover needs quotient_degree_bits == rate_bits and at most 2^%d ranks" % qdb)
+        self.n = 1 << info.degree_bits
+        self.nch, self.nzs, self.nq = info.num_challenges, info.num_challenges * (1 + info.num_partial_products), info.num_challenges * info.quotient_degree_factor
+        self.widths = [info.num_constants + info.num_routed_wires, info.num_wires, self.nzs, self.nq]
+        self.plans = [ShardPlan(w, info.degree_bits, info.rate_bits, info.cap_height, world) for w in self.widths]
+        self.count = self.plans[0].rows_per_rank
+        self.exchanges = [None] * 4
+        if use_peer and world > 1:
+            self.exchanges = [PeerExchange(p, rank, self.device, group=group, dist=dist) for p in self.plans]
+        if len(constants) != info.num_constants or len(sig) != info.num_routed_wires:
+            raise EngineError(_lib.ENG_ERR_INVALID, "expected %d constant and %d sigma columns" % (info.num_constants, info.num_routed_wires))
+        cols = [_u64(c) for c in constants] + sig
+        self.cs = self._commit(0, [cols[c] for c in self.plans[0].columns_of(rank)], True)
+
+    # ---- helpers ----
+    def _commit(self, k, local, is_values):
+        """local: this rank's columns of batch k -- a list of host columns or a [c_r][n] device tensor."""
+        plan, ex = self.plans[k], self.exchanges[k]
+        if isinstance(local, (list, tuple)) and ex is None:
+            local = self.ops.to_tensor(np.stack(local))
+        self._torch_sync()      # a tensor produced on torch's stream is consumed on the engine's stream
+        return ShardedPolynomialBatch.from_values(local, plan, self.rank, group=self.group, ops=self.ops, is_values=is_values,
+                                                  dist=self.dist, exchange=ex)
+
+    def _torch_sync(self):
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def _all_gather(self, t):
+        if self.world == 1:
+            return t
+        parts = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t, group=self.group)
+        out = self.torch.cat(parts)
+        self._torch_sync()      # the engine reads the gathered tensor on its own stream
+        return out
+
+    def _all_gather_object(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def _eval(self, batch, z):
+        c_r = batch.coeffs.shape[0]
+        out = np.empty((c_r, 2), np.uint64)
+        zz = _u64([int(z[0]), int(z[1])])
+        check(_lib.lib().eng_eval_ext_dev(C.c_void_p(batch.coeffs.data_ptr()), c_r, self.info.degree_bits, _ptr(zz), _ptr(out)))
+        return out
+
+    def fri_instance(self, zeta, gzeta):
+        """get_fri_instance: batch 0 = every polynomial of the four oracles at zeta, batch 1 = the Z's at g * zeta."""
+        from .plonky2 import FriInstanceInfo
+        all_polys = [(o, p) for o, w in enumerate(self.widths) for p in range(w)]
+        return FriInstanceInfo([(zeta, all_polys), (gzeta, [(2, p) for p in range(self.nch)])])
+
+    # ---- the proof ----
+    def prove(self, wire_cols_host, public_inputs_hash):
+        """wire_cols_host: all num_wires witness columns (host; every rank holds them, as every rank ran the generators or
+        received the witness).  Returns (proof blob, stage milliseconds); the blob is identical on every rank."""
+        import time
+        from .plonky2 import Challenger, FriParams
+        lib, info, torch = _lib.lib(), self.info, self.torch
+        if len(wire_cols_host) != info.num_wires:
+            raise EngineError(_lib.ENG_ERR_INVALID, "expected %d wire columns" % info.num_wires)
+        wires_host = [_u64(c) for c in wire_cols_host]
+        pi = _u64(public_inputs_hash)
+        marks = [time.perf_counter()]
+
+        def mark():
+            torch.cuda.synchronize()
+            marks.append(time.perf_counter())
+
+        ch = Challenger()
+        ch.observe_hash(self.digest)
+        ch.observe_hash(pi)
+        wires = self._commit(1, [wires_host[c] for c in self.plans[1].columns_of(self.rank)], True)
+        ch.observe_cap(wires.cap)
+        betas, gammas = _u64(ch.get_n_challenges(self.nch)), _u64(ch.get_n_challenges(self.nch))
+        mark()
+        # partial products: replicated (one pass over the routed wires + a scan over the rows; 6 ms at 2^22 rows)
+        zvals = self.ops.empty(self.nzs * self.n).view(self.nzs, self.n)
+        routed = (C.c_void_p * info.num_routed_wires)(*[wires_host[j].ctypes.data for j in range(info.num_routed_wires)])
+        check(lib.eng_partial_products_dev(self._h, routed, _ptr(betas), _ptr(gammas), C.c_void_p(zvals.data_ptr())))
+        mark()
+        zcols = self.plans[2].columns_of(self.rank)
+        zs = self._commit(2, zvals[zcols.start:zcols.stop].contiguous(), True)
+        del zvals
+        ch.observe_cap(zs.cap)
+        alphas = _u64(ch.get_n_challenges(self.nch))
+        mark()
+        # quotient: constraint evaluation on this rank's rows, all-gather, coset iNTT (replicated), commit of this rank's chunks
+        qv = self.ops.empty(self.nch * self.count)
+        check(lib.eng_quotient_values_shard_dev(self._h, C.c_void_p(self.cs.rows.data_ptr()), C.c_void_p(wires.rows.data_ptr()),
+                                                C.c_void_p(zs.rows.data_ptr()), self.log_world, self.rank, _ptr(pi), _ptr(betas),
+                                                _ptr(gammas), _ptr(alphas), C.c_void_p(qv.data_ptr())))
+        gathered = self._all_gather(qv)
+        qcoeffs = self.ops.empty(self.nq * self.n).view(self.nq, self.n)
+        check(lib.eng_quotient_coeffs_from_shards_dev(self._h, C.c_void_p(gathered.data_ptr()), self.log_world, C.c_void_p(qcoeffs.data_ptr())))
+        del gathered, qv
+        mark()
+        qcols = self.plans[3].columns_of(self.rank)
+        quot = self._commit(3, qcoeffs[qcols.start:qcols.stop].contiguous(), False)
+        del qcoeffs
+        ch.observe_cap(quot.cap)
+        zeta = ch.get_extension_challenge()
+        g_n = pow(_POWER_OF_TWO_GENERATOR, 1 << (32 - info.degree_bits), P)
+        gzeta = (zeta[0] * g_n % P, zeta[1] * g_n % P)
+        mark()
+        # opening set: every rank evaluates the polynomials of its column shards
+        batches = [self.cs, wires, zs, quot]
+        mine = [self._eval(b, zeta) for b in batches] + [self._eval(zs, gzeta)]
+        parts = self._all_gather_object(mine)
+        e_cs, e_w, e_z, e_q, e_zn = [np.concatenate([p[k] for p in parts]) for k in range(5)]
+        ncs, nch = info.num_constants, self.nch
+        op_consts, op_sig, op_zs, op_pp, op_zn = e_cs[:ncs], e_cs[ncs:], e_z[:nch], e_z[nch:], e_zn[:nch]
+        for v in (op_consts, op_sig, e_w, op_zs, op_pp, e_q, op_zn):
+            ch.observe_extension_elements(v.ravel())
+        mark()
+        # opening proofs: FRI layer 0 on this rank's rows, all-gather, the rest replicated; query openings from the row owners
+        alpha = _u64(ch.get_extension_challenge())
+        inst = self.fri_instance(zeta, gzeta).blob()
+        openings = _u64(np.concatenate([e_cs, e_w, e_z, e_q, op_zn]))
+        rows = (C.c_void_p * 4)(*[b.rows.data_ptr() for b in batches])
+        widths = (C.c_uint32 * 4)(*self.widths)
+        log_l = info.degree_bits + info.rate_bits
+        layer = self.ops.empty(2 * self.count)
+        check(lib.eng_fri_combine_shard_dev(_ptr(inst), rows, widths, 4, _ptr(openings), _ptr(alpha), log_l, self.log_world, self.rank,
+                                            C.c_void_p(layer.data_ptr())))
+        layer0 = self._all_gather(layer)
+        params = FriParams(info.degree_bits, info.rate_bits, info.cap_height, self.pow_bits, self.num_query_rounds)
+        blob = C.POINTER(C.c_uint64)()
+        blen = C.c_size_t(0)
+        x_idx = np.zeros(self.num_query_rounds, np.uint64)
+        check(lib.eng_fri_prove_from_layer_dev(C.c_void_p(layer0.data_ptr()), ch._h, params.as_array(), C.byref(blob), C.byref(blen), _ptr(x_idx)))
+        fri = np.ctypeslib.as_array(blob, shape=(blen.value,)).copy()
+        lib.eng_blob_free(blob)
+        del layer0, layer
+        mine = {}
+        for q, x in enumerate(int(v) for v in x_idx):
+            if batches[0].owns_leaf(x):
+                mine[q] = [(b.get(x), b.prove(x)) for b in batches]
+        merged = {}
+        for part in self._all_gather_object(mine):
+            merged.update(part)
+        fri = splice_initial_openings(fri, [merged[q] for q in range(self.num_query_rounds)])
+        mark()
+        proof = np.concatenate([_u64(wires.cap).ravel(), _u64(zs.cap).ravel(), _u64(quot.cap).ravel()] +
+                               [_u64(v).ravel() for v in (op_consts, op_sig, e_w, op_zs, op_zn, op_pp, e_q)] + [fri])
+        ms = [1e3 * (b_ - a_) for a_, b_ in zip(marks[:-1], marks[1:])]
+        ms.append(1e3 * (marks[-1] - marks[0]))
+        self.last_batches = batches      # keeps the exchange slots' batches alive for inspection
+        return proof, dict(zip(self.STAGES, ms))
+
+    def verify(self, public_inputs_hash, proof_blob):
+        from .plonky2 import verify
+        verify(self.blob, self.cs.cap, public_inputs_hash, proof_blob)
+
+    def close(self):
+        for ex in self.exchanges:
+            if ex is not None:
+                ex.close()
+        self.exchanges = [None] * 4
+        if getattr(self, "_h", None):
+            _lib.lib().eng_circuit_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().eng_circuit_free(self._h)
+                self._h = None
+        except Exception:
+            pass
