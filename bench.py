@@ -19,6 +19,7 @@ cpu_baseline   the C++/OpenMP oracle (a restatement of plonky2's CPU algorithm -
 import argparse
 import ctypes
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -101,14 +102,35 @@ def cpu_commit(cols, log_n, threads=None):
     return dt, stages, O.lib().orc_num_threads()
 
 
-def cpu_sample_log_n(cols, target_s=12.0, max_log_n=18):
-    """Largest sample (rows = 2^k <= 2^max_log_n) whose commit should take about target_s on this host."""
-    dt, _, _ = cpu_commit(cols, 12)
-    per_row = dt / (1 << 12)
+def cpu_sample_log_n(cols, target_s=12.0, max_log_n=20):
+    """Largest sample (rows = 2^k <= 2^max_log_n) whose commit should take about target_s on this host.  ONE rule for
+    the cpu_baseline object of the b200 arm and for every step of --impl reference (same target, same cap)."""
     k = 12
-    while k < max_log_n and per_row * (1 << (k + 1)) <= target_s:
-        k += 1
+    dt, _, _ = cpu_commit(cols, k)
+    while k < max_log_n:
+        step = max(1, min(max_log_n - k, int(math.floor(math.log2(max(target_s / max(dt, 1e-6), 1.0)))) - 1))
+        if dt * 2.0 > target_s:
+            break
+        k += step
+        dt, _, _ = cpu_commit(cols, k)      # re-measure: small samples over-estimate the per-row cost
+    while k > 12 and dt > 1.5 * target_s:
+        k -= 1
+        dt = dt / 2
     return k
+
+
+def cpu_sample_desc(cols, k, dt, stages, threads):
+    """The cpu_baseline object: value, the sample that was actually run, and the port's Poseidon rate per core."""
+    perms = num_perms(cols, 1 << k)
+    tree_s = stages.get("tree", 0.0)
+    d = {"value": b_ntt(cols, 1 << k) / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port", "sample_log_rows": k,
+         "sample": "one PolynomialBatch::from_values of %d columns x 2^%d rows (rate_bits 3, cap_height 4), %.1f s; C++/OpenMP "
+                   "restatement of plonky2's CPU algorithm (the Rust prover cannot be built here: no cargo, plonky2 not vendored)" % (cols, k, dt),
+         "stage_s": stages}
+    if tree_s > 0:
+        d["poseidon_perms_per_s_per_core"] = perms / tree_s / max(1, threads)
+        d["poseidon_us_per_perm_per_core"] = 1e6 * tree_s * max(1, threads) / perms
+    return d
 
 
 def run_reference(args):
@@ -119,7 +141,11 @@ def run_reference(args):
     if rank != 0:
         return
     cols = args.cols
-    k = min(args.log_n, cpu_sample_log_n(cols, target_s=max(4.0, 40.0 / max(1, args.steps + args.warmup))))
+    # every step is a bounded sample of the workload: the largest power-of-two row count (<= the workload's) whose commit
+    # takes about 12 s on this host -- the same rule the b200 arm uses for its cpu_baseline object.  The row count that
+    # was actually run is printed in config.sample_log_rows; value is a rate (GB/s of algorithmic commit bytes), which
+    # is what makes a sample comparable with the full-size GPU step.
+    k = min(args.log_n, cpu_sample_log_n(cols))
     for _ in range(args.warmup):
         cpu_commit(cols, k)
     t = []
@@ -129,27 +155,40 @@ def run_reference(args):
         t.append(dt)
     sec = sum(t) / len(t)
     gbs = b_ntt(cols, 1 << k) / sec / 1e9
+    cfg = workload_config(cols, args.log_n, args.gpus)
+    cfg["sample_log_rows"] = k
+    cfg["sample_note"] = ("CPU arm: each step commits %d columns x 2^%d rows (a bounded sample of the 2^%d-row workload, about %.0f s per "
+                          "step on %d threads); rates, not times, are comparable" % (cols, k, args.log_n, sec, threads))
     line = {
         "impl": "reference", "metric": "commit_throughput", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic (SplitMix64 witness columns)",
-        "config": workload_config(cols, args.log_n, args.gpus),
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
-                         "sample": "one PolynomialBatch::from_values of %d columns x 2^%d rows (rate_bits 3, cap_height 4) per step; "
-                                   "C++/OpenMP restatement of plonky2's CPU algorithm, not the Rust prover" % (cols, k),
-                         "stage_s": stages},
+        "config": cfg,
+        "cpu_baseline": cpu_sample_desc(cols, k, sec, stages, threads),
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def proof_section(E, log_n, reps=4):
+def oracle_verify(blob, cs_cap, pi_hash, proof):
+    """Checker use of the oracle (allowed outside the timed region): its restatement of plonky2's verifier on a bench proof."""
+    try:
+        from oracle import oracle as O
+        return O.Circuit(blob).verify(cs_cap, pi_hash, proof) == 0
+    except Exception as ex:   # noqa: BLE001
+        return "unavailable: %r" % (ex,)
+
+
+def proof_section(E, log_n, reps=4, all_gates=False):
     """BASELINE.json's first metric: proof wall-time (s).  The real eth-lc circuit cannot be built here (it needs
     plonky2's Rust front-end), so this is the circuit-SHAPED synthetic proof of SURVEY.md 8(d): 135 wires, 80 routed,
-    84 constants||sigmas columns, the five core gates (half the rows are PoseidonGate), standard_recursion_config
-    (rate_bits 3, cap_height 4, 16-bit grind, 28 queries), witness on the host, everything after witness generation on
-    the GPU through eng_prove.  Wall clock around the call with host wire columns (H2D inside)."""
-    s = E.synth_circuit(log_n, seed=1)
+    selectors + 2 constants + 80 sigmas, standard_recursion_config (rate_bits 3, cap_height 4, 16-bit grind, 28 queries),
+    witness on the host, everything after witness generation on the GPU through eng_prove.  Gate set: the five core gates
+    (half the rows PoseidonGate), or with all_gates the 18 gate kinds of gate_lib.h (recursion + plonky2_crypto u32 gates,
+    evaluated from bytecode) -- the gate mix of the real circuit.  Wall clock around the call with host wire columns (H2D
+    inside).  Every proof is verified (product verifier + the oracle's restatement of plonky2's)."""
+    import hashlib
+    s = E.synth_circuit_v2(log_n, seed=1) if all_gates else E.synth_circuit(log_n, seed=1)
     t0 = time.perf_counter()
     circ = E.Circuit.build(s)
     E.synchronize()
@@ -160,15 +199,140 @@ def proof_section(E, log_n, reps=4):
         t = time.perf_counter()
         proof, st = circ.prove(wires, s["pi_hash"])
         walls.append(time.perf_counter() - t)
-        if i and (best is None or walls[-1] < best):     # the first call pays table construction and pool growth
+        if i and (best is None or walls[-1] < best):     # the first call pays whatever the process has not warmed yet
             best, stages = walls[-1], st
     if best is None:
         best, stages = walls[0], st
+    verified = {"engine": False, "oracle": None}
+    try:
+        circ.verify(s["pi_hash"], proof)
+        verified["engine"] = True
+    except Exception as ex:   # noqa: BLE001
+        verified["engine"] = repr(ex)[:200]
+    verified["oracle"] = oracle_verify(s["blob"], circ.constants_sigmas.merkle_tree.cap, s["pi_hash"], proof)
     return {"metric": "synthetic_proof_wall_time", "value": best, "unit": "s", "all_runs_s": walls,
             "higher_is_better": False, "log_rows": log_n,
-            "config": "circuit-shaped synthetic proof, 2^%d rows x 135 wires, 5 core gates, standard_recursion_config" % log_n,
-            "build_constants_sigmas_commit_s": build_s, "stage_ms": stages, "proof_u64_words": int(proof.size),
+            "config": "circuit-shaped synthetic proof, 2^%d rows x 135 wires, %s, standard_recursion_config" % (
+                log_n, "18 gate kinds (core + recursion + u32, bytecode)" if all_gates else "5 core gates"),
+            "build_constants_sigmas_commit_s": build_s, "first_call_s": build_s + walls[0],
+            "first_call_note": "Circuit.build (constants||sigmas commit + memory-pool growth for one proof) + the first eng_prove of the process",
+            "stage_ms": stages, "proof_u64_words": int(proof.size), "proof_sha256": hashlib.sha256(proof.tobytes()).hexdigest(),
+            "verified": verified,
             "reference_published": "~300 s for the real 2^22-row circuit on 32 vCPU (README.md:71); not comparable 1:1"}
+
+
+def sharded_proof_section(E, log_n, rank, world, local_rank, reps=3, compare_single=True):
+    """N > 1: the same synthetic proof through ShardedProver (parallel.py): strong scaling of ONE proof over the ranks.
+    Every rank builds the same synthetic circuit and witness (seeded).  The proof is verified and, on rank 0, compared
+    word for word with the single-GPU eng_prove of the same witness."""
+    import hashlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    s = E.synth_circuit(log_n, seed=1)
+    t0 = time.perf_counter()
+    pr = E.ShardedProver(s["blob"], s["constants"], s["sigmas"], rank, world, device=torch.device("cuda", local_rank))
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    walls, stages = [], {}
+    for i in range(reps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        proof, st = pr.prove(s["wires"], s["pi_hash"])
+        walls.append(time.perf_counter() - t)
+        if i == reps - 1:
+            stages = st
+    tw = torch.tensor(walls, dtype=torch.float64, device="cuda")
+    dist.all_reduce(tw, op=dist.ReduceOp.MAX)          # a proof is done when the slowest rank has it
+    walls = tw.tolist()
+    sha = hashlib.sha256(proof.tobytes()).hexdigest()
+    shas = [None] * world
+    dist.all_gather_object(shas, sha)
+    out = None
+    if rank == 0:
+        verified = {"engine": False, "oracle": None, "identical_on_all_ranks": len(set(shas)) == 1}
+        try:
+            pr.verify(s["pi_hash"], proof)
+            verified["engine"] = True
+        except Exception as ex:   # noqa: BLE001
+            verified["engine"] = repr(ex)[:200]
+        verified["oracle"] = oracle_verify(s["blob"], pr.cs.cap, s["pi_hash"], proof)
+        out = {"metric": "synthetic_proof_wall_time", "value": min(walls[1:]) if len(walls) > 1 else walls[0], "unit": "s", "all_runs_s": walls,
+               "higher_is_better": False, "log_rows": log_n, "n_gpus": world, "scaling": "strong",
+               "config": "circuit-shaped synthetic proof, 2^%d rows x 135 wires, 5 core gates, standard_recursion_config; ONE proof "
+                         "over %d GPUs (ShardedProver: column/row-sharded commits, row-local quotient and FRI layer 0)" % (log_n, world),
+               "build_constants_sigmas_commit_s": build_s, "stage_ms": stages, "proof_sha256": sha, "verified": verified}
+    pr.close()
+    if rank == 0 and compare_single:
+        try:
+            circ = E.Circuit.build(s)
+            ref, _ = circ.prove(list(s["wires"]), s["pi_hash"])
+            out["verified"]["equals_single_gpu_proof"] = bool(ref.shape == proof.shape and (ref == proof).all())
+            del circ
+            E.release_cached()
+        except Exception as ex:   # noqa: BLE001
+            out["verified"]["equals_single_gpu_proof"] = "not compared: %r" % (ex,)
+    dist.barrier()
+    return out
+
+
+def peer_parity_check(E, plan_cols, rank, world, local_rank, use_peer):
+    """N > 1, before timing: a 135 x 2^14 commit through the REAL exchange (CUDA-IPC peer stores, or NCCL all-to-all) against
+    (a) the single-GPU engine path and (b) the oracle, on rank 0: cap, every digest, Merkle paths (VERDICT r1 task 1b)."""
+    import hashlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    log_n = 14
+    n = 1 << log_n
+    plan = E.ShardPlan(plan_cols, log_n, RATE_BITS, CAP_HEIGHT, world)
+    ex = None
+    if use_peer:
+        ex = E.PeerExchange(plan, rank, torch.device("cuda", local_rank))
+    cols = plan.columns_of(rank)
+    vals = E.splitmix_columns(len(cols), n, first_col=cols.start)
+    dev = torch.from_numpy(vals.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    b = E.ShardedPolynomialBatch.from_values(dev, plan, rank, exchange=ex)
+    digs = [None] * world
+    dist.all_gather_object(digs, hashlib.sha256(np.ascontiguousarray(b.local_digests).tobytes()).hexdigest())
+    L = n << RATE_BITS
+    probe = [0, 1, L // 2 + 77, L - 1] + [r * plan.rows_per_rank + 5 for r in range(world)]
+    mine = {k: (b.get(k).tolist(), b.prove(k).tolist()) for k in probe if b.owns_leaf(k)}
+    opened = [None] * world
+    dist.all_gather_object(opened, mine)
+    res = None
+    if rank == 0:
+        full = E.splitmix_columns(plan_cols, n)
+        single = E.PolynomialBatch.from_values(list(full), RATE_BITS, False, CAP_HEIGHT)
+        sd = single.merkle_tree.digests
+        per = sd.shape[0] // world
+        res = {"shape": "%d columns x 2^%d rows, rate_bits 3, cap_height 4, %d ranks" % (plan_cols, log_n, world),
+               "exchange": "peer stores (CUDA IPC)" if ex is not None else "NCCL all_to_all",
+               "cap_equals_single_gpu": bool((np.array(b.cap) == single.merkle_tree.cap).all()),
+               "digests_equal_single_gpu": all(digs[r] == hashlib.sha256(np.ascontiguousarray(sd[r * per:(r + 1) * per]).tobytes()).hexdigest() for r in range(world)),
+               "cap_sha256": hashlib.sha256(np.ascontiguousarray(b.cap).tobytes()).hexdigest()}
+        ok = True
+        for part in opened:
+            for k, (leaf, path) in part.items():
+                ok = ok and leaf == single.merkle_tree.get(k).tolist() and path == single.merkle_tree.prove(k).tolist()
+        res["leaves_and_paths_equal_single_gpu"] = bool(ok)
+        try:
+            from oracle import oracle as O
+            o = O.Batch.from_values(full, RATE_BITS, CAP_HEIGHT)
+            res["cap_equals_oracle"] = bool((np.array(b.cap) == o.cap).all())
+            res["digests_equal_oracle"] = bool((sd == o.digests).all())
+            res["paths_equal_oracle"] = all(path == o.prove(k).tolist() for part in opened for k, (leaf, path) in part.items())
+        except Exception as exn:   # noqa: BLE001
+            res["oracle"] = "unavailable: %r" % (exn,)
+        res["peer_exchange"] = "ok" if all(v for v in res.values() if isinstance(v, bool)) else "MISMATCH"
+        single.close()
+    del b
+    if ex is not None:
+        ex.close()
+    dist.barrier()
+    return res
 
 
 def dist_roofline(stages, cols, n, world):
@@ -191,12 +355,12 @@ def exchange_close(exchange):
         exchange.close()
 
 
-def workload_config(cols, log_n, gpus):
+def workload_config(cols, log_n, gpus, scaling="weak"):
     return {"workload": "PolynomialBatch::from_values commit, %d Goldilocks columns x 2^%d rows, rate_bits=3, cap_height=4 "
                         "(BASELINE.json configs[1])" % (cols, log_n),
             "columns": cols, "log_rows": log_n, "rate_bits": RATE_BITS, "cap_height": CAP_HEIGHT,
             "parallelism": "1 GPU" if gpus == 1 else "%d GPUs: column-sharded iNTT/LDE -> all-to-all -> row-sharded hashing -> cap "
-                                                      "all-gather; rows scale with N (2^20 per GPU)" % gpus,
+                                                      "all-gather; %s" % (gpus, "rows scale with N (2^20 per GPU)" if scaling == "weak" else "rows fixed (strong scaling)"),
             "l2": "inputs (%.2f GB per step) are larger than the 126 MB L2; no flush needed" % (8 * cols * (1 << log_n) / 1e9)}
 
 
@@ -211,6 +375,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--proof-log-n", type=int, default=20, help="rows (log2) of the synthetic circuit-shaped proof; 0 = skip")
     ap.add_argument("--proof-full-log-n", type=int, default=22, help="rows (log2) of the full-size synthetic proof; 0 = skip")
+    ap.add_argument("--dist-proof-log-n", type=int, default=20, help="N > 1: rows (log2) of the ONE synthetic proof run over all ranks (strong scaling); 0 = skip")
+    ap.add_argument("--dist-proof-full-log-n", type=int, default=22, help="N > 1: the eth-lc-sized proof (2^22 rows) over all ranks; 0 = skip")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1 commit: weak = 2^log_n rows PER GPU (default, the driver's scaling run); strong = 2^log_n rows in total")
+    ap.add_argument("--all-gates-proof-log-n", type=int, default=20, help="N = 1: rows (log2) of the synthetic proof over all 18 gate kinds; 0 = skip")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: column->row exchange fused into the LDE's last pass as NVLink peer stores (default), or NCCL all-to-all")
     args = ap.parse_args()
@@ -236,8 +405,14 @@ def main():
     cols = args.cols
     # N = 1: BASELINE configs[1].  N > 1: the same commit column-sharded over the ranks with one all-to-all
     # (parallel.py); rows scale with N so that the per-GPU work is fixed (weak scaling, configs[4] sweep shape).
-    log_n = args.log_n + (world.bit_length() - 1)
+    log_n = args.log_n + (world.bit_length() - 1 if args.scaling == "weak" else 0)
     n = 1 << log_n
+    parity = None
+    if distributed:      # real-transport parity before anything is timed
+        try:
+            parity = peer_parity_check(E, cols, rank, world, local_rank, args.exchange == "peer")
+        except Exception as ex:   # noqa: BLE001
+            parity = {"peer_exchange": "check failed to run: %r" % (ex,)}
     plan = E.ShardPlan(cols, log_n, RATE_BITS, CAP_HEIGHT, world) if distributed else None
     exchange = None
     if distributed and args.exchange == "peer":
@@ -327,6 +502,25 @@ def main():
     ms_total, ms_e2e = times.tolist()
 
     int_peak = E.measure_int_peak()
+    import hashlib
+    cap_sha = hashlib.sha256(np.ascontiguousarray(cap_e2e).tobytes()).hexdigest()
+    dist_proofs = {}
+    if distributed:
+        # release the commit bench's buffers before the proofs (every rank; the exchange of the commit stays open until the end)
+        try:
+            del dev
+            torch.cuda.empty_cache()
+            E.release_cached()
+        except Exception:   # noqa: BLE001
+            pass
+        for key, lg in (("proof", args.dist_proof_log_n), ("proof_full_size", args.dist_proof_full_log_n)):
+            if not lg:
+                continue
+            try:     # collective: every rank takes part; a failure on any rank must not lose the commit line
+                dist_proofs[key] = sharded_proof_section(E, lg, rank, world, local_rank)
+            except Exception as ex:   # noqa: BLE001
+                dist_proofs[key] = {"error": repr(ex)[:300]}
+                break
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         bytes_step = b_ntt(cols, n)
@@ -337,17 +531,18 @@ def main():
         if distributed:
             line = {
                 "metric": "commit_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic (SplitMix64 witness columns)",
-                "config": workload_config(cols, log_n, world),
+                "config": workload_config(cols, log_n, world, args.scaling),
                 "e2e": {"value": e2e_value, "unit": "GB/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": 8 * cols * n, "d2h_bytes_per_step": (32 << CAP_HEIGHT) * world},
-                "gpu_launches": launches, "clocks": clocks, "cap0": "%016x" % int(cap_e2e[0][0]),
+                "gpu_launches": launches, "clocks": clocks, "cap_sha256": cap_sha, "parity_check": parity,
                 "stage_ms": stages, "roofline": dist_roofline(stages, cols, n, world),
                 "exchange": ("fused: the LDE's last pass stores %.2f GB per rank into the peers' leaf matrices (NVLink P2P, CUDA IPC); NCCL carries two "
                              "barriers and the cap all_gather" if exchange is not None else
                              "all_to_all_single of %.2f GB per rank (NCCL), cap all_gather") % (8 * len(my_cols) * (n << RATE_BITS) * (world - 1) / world / 1e9),
             }
+            line.update({k: v for k, v in dist_proofs.items() if v is not None})
             print(json.dumps(line), flush=True)
             exchange_close(exchange)
             dist.destroy_process_group()
@@ -385,7 +580,7 @@ def main():
                              "note": "integer-issue bound, not HBM bound: alu pipe 57-69 % of peak at 54-61 % issue activity, DRAM 7-16 % "
                                      "(profiles/r01_ntt_v3.md); reported against the HBM roof because BASELINE.json asks for it", "kernel_ms": ntt_ms, "algorithmic_bytes": b_ntt(cols, n)},
             "clocks": clocks,
-            "cap0": "%016x" % int(cap_e2e[0][0]),
+            "cap_sha256": cap_sha,
         }
         # the proof sections are extras next to the headline metric: a failure there must not lose the commit line
         if args.proof_log_n:
@@ -393,6 +588,12 @@ def main():
                 line["proof"] = proof_section(E, args.proof_log_n)
             except Exception as ex:   # noqa: BLE001
                 line["proof"] = {"error": repr(ex)[:300]}
+        if args.all_gates_proof_log_n:
+            # the gate mix of the real circuit: 18 gate kinds evaluated from bytecode (gate_vm.h)
+            try:
+                line["proof_all_gates"] = proof_section(E, args.all_gates_proof_log_n, reps=3, all_gates=True)
+            except Exception as ex:   # noqa: BLE001
+                line["proof_all_gates"] = {"error": repr(ex)[:300]}
         if args.proof_full_log_n:
             # the eth-lc circuit's own size (~2.98 M constraints => 2^22 rows, BASELINE configs[3]); same synthetic gate set
             try:
@@ -404,12 +605,9 @@ def main():
                 E.release_cached()    # give the device memory of the proof sections back before the host-side baseline
             except Exception:         # noqa: BLE001
                 pass
-            k = cpu_sample_log_n(cols)
+            k = min(args.log_n, cpu_sample_log_n(cols))
             dt, cpu_stages, threads = cpu_commit(cols, k)
-            line["cpu_baseline"] = {"value": b_ntt(cols, 1 << k) / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
-                                    "sample": "one commit of %d columns x 2^%d rows (rate_bits 3, cap_height 4), %.1f s; C++/OpenMP "
-                                              "restatement of plonky2's CPU algorithm, not the Rust prover" % (cols, k, dt),
-                                    "stage_s": cpu_stages}
+            line["cpu_baseline"] = cpu_sample_desc(cols, k, dt, cpu_stages, threads)
         print(json.dumps(line), flush=True)
     if distributed:
         exchange_close(exchange)      # collective: every rank

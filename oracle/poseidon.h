@@ -47,47 +47,77 @@ static inline void orc_poseidon_naive(u64 s[12]) {
     }
 }
 
-/* Production form of plonky2 (partial rounds through the sparse factorisation); identical outputs. */
+/* ---- lazily reduced helpers of the production form: values are ANY u64 representative, canonicalised once at the end
+ * (plonky2 does the same: GoldilocksField is non-canonical internally).  Only orc_poseidon uses them. ---- */
+static inline u64 orc_red128(u128 x) {            /* gl_reduce128 without the final canonicalisation */
+    u64 lo = (u64)x, hi = (u64)(x >> 64);
+    u64 hh = hi >> 32, hl = hi & GL_EPS;
+    u64 t0;
+    u64 borrow = __builtin_sub_overflow(lo, hh, &t0);
+    t0 -= (0 - borrow) & GL_EPS;
+    u64 t1 = hl * GL_EPS;
+    u64 t2;
+    u64 carry = __builtin_add_overflow(t0, t1, &t2);
+    t2 += (0 - carry) & GL_EPS;
+    return t2;
+}
+static inline u64 orc_mulr(u64 a, u64 b) { return orc_red128((u128)a * b); }
+static inline u64 orc_sbox7r(u64 x) {
+    u64 x2 = orc_mulr(x, x), x4 = orc_mulr(x2, x2), x3 = orc_mulr(x, x2);
+    return orc_mulr(x3, x4);
+}
+static inline u64 orc_addc(u64 s, u64 c) {         /* s any u64, c canonical: one wrap at most */
+    u64 t = s + c;
+    return t + ((t < s) ? GL_EPS : 0);
+}
+static inline void orc_mds_r(u64 s[12]) {
+    u64 lo[24], hi[24], o[12];
+    for (int i = 0; i < 12; i++) { lo[i] = lo[i + 12] = s[i] & GL_EPS; hi[i] = hi[i + 12] = s[i] >> 32; }
+    for (int r = 0; r < 12; r++) {
+        u64 al = 0, ah = 0;
+        for (int i = 0; i < 12; i++) { al += lo[i + r] * ORC_MDS_CIRC[i]; ah += hi[i + r] * ORC_MDS_CIRC[i]; }
+        if (r == 0) { al += lo[0] * POSEIDON_MDS_DIAG0; ah += hi[0] * POSEIDON_MDS_DIAG0; }
+        o[r] = orc_red128((u128)al + ((u128)ah << 32));
+    }
+    for (int r = 0; r < 12; r++) s[r] = o[r];
+}
+/* sum of up to 12 products of u64s, accumulated as (low words, high words): no carry tracking, 2^64 = eps at the end
+ * (what plonky2's reduce_u160 / mds_partial_layer_fast achieve with a u160 accumulator) */
+#define ORC_DOT_ACC(alo, ahi, a, b) do { u128 t__ = (u128)(a) * (b); (alo) += (u64)t__; (ahi) += (u64)(t__ >> 64); } while (0)
+static inline u64 orc_dot_finish(u128 alo, u128 ahi) { return orc_red128((u128)orc_red128(alo) + (u128)orc_red128(ahi) * GL_EPS); }
+
+/* Production form of plonky2 (partial rounds through the sparse factorisation); identical outputs.  The timed CPU
+ * baseline runs this one; orc_poseidon_naive above is the independent form it is checked against (tests/test_oracle.py). */
 static inline void orc_poseidon(u64 s[12]) {
-    for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
     int rnd = 0;
     for (int k = 0; k < 4; k++, rnd++) {
-        for (int i = 0; i < 12; i++) s[i] = orc_sbox7(gl_add(s[i], POSEIDON_RC[12 * rnd + i]));
-        orc_mds(s);
+        for (int i = 0; i < 12; i++) s[i] = orc_sbox7r(orc_addc(s[i], POSEIDON_RC[12 * rnd + i]));
+        orc_mds_r(s);
     }
-    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POSEIDON_FAST_FIRST[i]);
+    for (int i = 0; i < 12; i++) s[i] = orc_addc(s[i], POSEIDON_FAST_FIRST[i]);
     {
         u64 o[11];
         for (int i = 0; i < 11; i++) {
-            u128 acc = 0; u64 carry = 0;
-            for (int j = 0; j < 11; j++) {
-                u128 t = (u128)POSEIDON_FAST_INIT[11 * i + j] * s[j + 1];
-                acc += t; carry += acc < t;
-            }
-            /* acc + carry*2^128 ; 2^128 = 2^64*2^64 = eps^2 mod p */
-            u64 r = gl_reduce128(acc);
-            if (carry) r = gl_add(r, gl_mul(carry, gl_mul(GL_EPS, GL_EPS)));
-            o[i] = r;
+            u128 alo = 0, ahi = 0;
+            for (int j = 0; j < 11; j++) ORC_DOT_ACC(alo, ahi, POSEIDON_FAST_INIT[11 * i + j], s[j + 1]);
+            o[i] = orc_dot_finish(alo, ahi);
         }
         for (int i = 0; i < 11; i++) s[i + 1] = o[i];
     }
     for (int r = 0; r < POSEIDON_PARTIAL_ROUNDS; r++) {
-        u64 s0 = gl_add(orc_sbox7(s[0]), POSEIDON_FAST_K[r]);
-        u128 acc = (u128)s0 * 25; u64 carry = 0;
-        for (int i = 0; i < 11; i++) {
-            u128 t = (u128)POSEIDON_FAST_ROW[11 * r + i] * s[i + 1];
-            acc += t; carry += acc < t;
-        }
-        u64 d = gl_reduce128(acc);
-        if (carry) d = gl_add(d, gl_mul(carry, gl_mul(GL_EPS, GL_EPS)));
-        for (int i = 0; i < 11; i++) s[i + 1] = gl_add(s[i + 1], gl_mul(POSEIDON_FAST_COL[11 * r + i], s0));
+        const u64 s0 = orc_addc(orc_sbox7r(s[0]), POSEIDON_FAST_K[r]);
+        u128 alo = (u128)s0 * 25, ahi = 0;
+        for (int i = 0; i < 11; i++) ORC_DOT_ACC(alo, ahi, POSEIDON_FAST_ROW[11 * r + i], s[i + 1]);
+        const u64 d = orc_dot_finish(alo, ahi);
+        for (int i = 0; i < 11; i++) s[i + 1] = orc_red128((u128)POSEIDON_FAST_COL[11 * r + i] * s0 + s[i + 1]);
         s[0] = d;
     }
     rnd += POSEIDON_PARTIAL_ROUNDS;
     for (int k = 0; k < 4; k++, rnd++) {
-        for (int i = 0; i < 12; i++) s[i] = orc_sbox7(gl_add(s[i], POSEIDON_RC[12 * rnd + i]));
-        orc_mds(s);
+        for (int i = 0; i < 12; i++) s[i] = orc_sbox7r(orc_addc(s[i], POSEIDON_RC[12 * rnd + i]));
+        orc_mds_r(s);
     }
+    for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
 }
 
 /* hash_n_to_m_no_pad with m = 4: overwrite-mode sponge, rate 8 [hashing.rs] */
