@@ -85,6 +85,8 @@ _SIGNATURES = {
     "eng_circuit_free": [_vp],
     "eng_circuit_new_sharded": [_vp, C.POINTER(_vp), C.POINTER(_vp)],
     "eng_partial_products_dev": [_vp, C.POINTER(_vp), _vp, _vp, _vp],
+    "eng_partial_products_from_dev": [_vp, _vp, _vp, _vp, _vp],
+    "eng_h2d_columns": [C.POINTER(_vp), C.c_uint32, C.c_uint64, _vp],
     "eng_quotient_values_shard_dev": [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp],
     "eng_quotient_coeffs_from_shards_dev": [_vp, _vp, C.c_uint32, _vp],
     "eng_eval_ext_dev": [_vp, C.c_uint32, C.c_uint32, _vp, _vp],

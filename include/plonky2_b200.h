@@ -273,6 +273,11 @@ eng_status eng_circuit_new_sharded(const uint64_t *blob, const uint64_t *const *
 /* a5 with the result left on the device: out_dev [num_challenges * (1 + num_partial_products)][n] */
 eng_status eng_partial_products_dev(const eng_circuit *c, const uint64_t *const *wire_cols_host, const uint64_t *betas,
                                     const uint64_t *gammas, uint64_t *out_dev);
+/* the same from routed wire values already on the device (the sharded prover all-gathers them from the ranks' column shards) */
+eng_status eng_partial_products_from_dev(const eng_circuit *c, const uint64_t *wires_dev, const uint64_t *betas, const uint64_t *gammas,
+                                         uint64_t *out_dev);
+/* host columns -> one device array [num_cols][n] through the engine's pinned staging pipeline */
+eng_status eng_h2d_columns(const uint64_t *const *cols_host, uint32_t num_cols, uint64_t n, uint64_t *dst_dev);
 /* a6 on row shard `shard` of 2^log_shards: quotient values at LDE positions [shard * L/G, (shard + 1) * L/G) from this rank's
  * leaf matrices ([cols][L/G] column-major) -> out_dev [num_challenges][L/G], position order.  Needs quotient_degree_bits ==
  * rate_bits and G <= 2^quotient_degree_bits. */
