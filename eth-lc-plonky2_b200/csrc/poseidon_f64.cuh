@@ -238,52 +238,7 @@ GL_HD void pf_pow7(u64 x, double &lo, double &hi) {
     hi = d1 + d2;
 }
 
-// out = init + M * in, per half.  M = circ(CIRC) + 8 e0 e0^T.
-// PF_MDS_ORDER 0: row by row (12 chains of 12).  1: column by column -- 12 consecutive DFMAs share the multiplicand
-// register, which the operand-reuse cache serves (a DFMA with three fresh register operands issues every 3 cycles,
-// one with a reused operand every 2.2: tools/bench/pipe_bench2.cu).
-#ifndef PF_MDS_ORDER
-#define PF_MDS_ORDER 1
-#endif
-GL_HD void pf_mds(const double (&xl)[12], const double (&xh)[12], int layer, double (&al)[12], double (&ah)[12]) {
-#if PF_MDS_ORDER == 0
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        double l = PF_T(full_init)[layer][r][0], h = PF_T(full_init)[layer][r][1];
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            l = pf_fma(xl[(i + r) % 12], PF_T(circ)[i], l);
-            h = pf_fma(xh[(i + r) % 12], PF_T(circ)[i], h);
-        }
-        if (r == 0) {
-            l = pf_fma(xl[0], 8.0, l);
-            h = pf_fma(xh[0], 8.0, h);
-        }
-        al[r] = l;
-        ah[r] = h;
-    }
-#else
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        al[r] = PF_T(full_init)[layer][r][0];
-        ah[r] = PF_T(full_init)[layer][r][1];
-    }
-#pragma unroll
-    for (int k = 0; k < 12; k++) {
-#pragma unroll
-        for (int r = 0; r < 12; r++) al[r] = pf_fma(xl[k], PF_T(circ)[(k - r + 12) % 12], al[r]);
-#pragma unroll
-        for (int r = 0; r < 12; r++) ah[r] = pf_fma(xh[k], PF_T(circ)[(k - r + 12) % 12], ah[r]);
-    }
-    al[0] = pf_fma(xl[0], 8.0, al[0]);
-    ah[0] = pf_fma(xh[0], 8.0, ah[0]);
-#endif
-}
-
 // y = init + circ(c) x as a split convolution (see PsdF64Tables::sc1).  cc = split coefficients, init = split constants.
-#ifndef PF_SPLIT
-#define PF_SPLIT 1
-#endif
 GL_HD void pf_circ12(const double (&x)[12], const double *cc, const double *init, double (&y)[12]) {
     double P[6], Q[6], PP[3], PQ[3], U[6];
 #pragma unroll
@@ -348,14 +303,10 @@ GL_HD void pf_full_round(u64 (&s)[12], int layer) {
     }
 #endif
     double al[12], ah[12];
-#if PF_SPLIT
     pf_circ12(xl, PF_T(sc1), PF_T(full_init_s)[layer][0], al);
     pf_circ12(xh, PF_T(sc1), PF_T(full_init_s)[layer][1], ah);
     al[0] = pf_fma(xl[0], 8.0, al[0]);
     ah[0] = pf_fma(xh[0], 8.0, ah[0]);
-#else
-    pf_mds(xl, xh, layer, al, ah);
-#endif
 #pragma unroll
     for (int r = 0; r < 12; r++) s[r] = pf_fold(al[r], ah[r]);
 }
@@ -377,7 +328,6 @@ GL_HD void pf_partial_rounds(u64 (&s)[12]) {
         for (int j = 1; j < 12; j++) pf_renorm(al[j], ah[j]);
         pf_pow7(a, al[0], ah[0]);                       // W
         double t0l = PF_T(pair_t0)[p][0], t0h = PF_T(pair_t0)[p][1];
-#if PF_SPLIT
         // T0 = (C W)[0] + 8 W_0 + const;  M^2 W = circ(c2) W + W_0 * (8 C e_0) + e_0 * 8 (T0 - const)
 #pragma unroll
         for (int j = 0; j < 12; j++) {
@@ -397,42 +347,6 @@ GL_HD void pf_partial_rounds(u64 (&s)[12]) {
         }
         nl[0] = pf_fma(t0l, 8.0, nl[0]);
         nh[0] = pf_fma(t0h, 8.0, nh[0]);
-#else
-#pragma unroll
-        for (int j = 0; j < 12; j++) {
-            t0l = pf_fma(al[j], PF_T(m_row0)[j], t0l);
-            t0h = pf_fma(ah[j], PF_T(m_row0)[j], t0h);
-        }
-        const u64 b = pf_fold(t0l, t0h);                // lane 0 entering the second S-box (RC included)
-        double nl[12], nh[12];                          // M^2 W + K: independent of b, overlaps the S-box below
-#if PF_MDS_ORDER == 0
-#pragma unroll
-        for (int r = 0; r < 12; r++) {
-            double l = PF_T(pair_k)[p][r][0], h = PF_T(pair_k)[p][r][1];
-#pragma unroll
-            for (int j = 0; j < 12; j++) {
-                l = pf_fma(al[j], PF_T(m2)[r][j], l);
-                h = pf_fma(ah[j], PF_T(m2)[r][j], h);
-            }
-            nl[r] = l;
-            nh[r] = h;
-        }
-#else
-#pragma unroll
-        for (int r = 0; r < 12; r++) {
-            nl[r] = PF_T(pair_k)[p][r][0];
-            nh[r] = PF_T(pair_k)[p][r][1];
-        }
-#pragma unroll
-        for (int jj = 0; jj < 12; jj++) {
-            const int j = (jj + 1) % 12;                // lane 0 (the S-box output) last
-#pragma unroll
-            for (int r = 0; r < 12; r++) nl[r] = pf_fma(al[j], PF_T(m2)[r][j], nl[r]);
-#pragma unroll
-            for (int r = 0; r < 12; r++) nh[r] = pf_fma(ah[j], PF_T(m2)[r][j], nh[r]);
-        }
-#endif
-#endif
         double bl, bh;
         pf_pow7(b, bl, bh);
         const double dl = bl - t0l, dh = bh - t0h;      // (b' - b) + B as a pair

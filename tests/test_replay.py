@@ -75,7 +75,7 @@ def test_poseidon_fp64_formulation(emu, oracle):
 
 
 CASES = [(3, 0, 1, 0), (3, 1, 1, 1), (5, 2, 2, 0), (9, 3, 1, 1), (3, 3, 3, 2), (135, 4, 3, 4), (7, 5, 3, 2), (9, 7, 2, 3),
-         (2, 10, 1, 4), (3, 12, 2, 4), (3, 13, 1, 4), (2, 13, 3, 0), (3, 14, 2, 4)]
+         (2, 10, 1, 4), (3, 12, 2, 4), (3, 13, 1, 4), (2, 13, 3, 0), (3, 14, 2, 4), (1, 15, 1, 2)]   # 15: odd two-pass split (7 + 8)
 
 
 @pytest.mark.parametrize("C_,log_n,r,h", CASES)
