@@ -306,12 +306,29 @@ def test_fused_exchange_stores_emulated_on_one_gpu(engine, oracle, world, log_n,
     ref = oracle.Batch.from_values(vals, r, h)
     plan = E.ShardPlan(C_, log_n, r, h, world)
     ops = E.EngineOps(torch.device("cuda", 0))
-    mats = [ops.empty(C_ * plan.rows_per_rank) for _ in range(world)]          # rank g's [C][L/G]
+    # compute-sanitizer is closed on this pool, so the test carries its own out-of-bounds detector: every buffer a kernel
+    # stores into (the "peer" leaf matrices, the scratch, the coefficients) sits between two guard bands holding a canary,
+    # and the canaries are checked after every rank's transform (a store one element outside any buffer trips it).
+    GUARD, CANARY = 4096, -0x0123456789ABCDEF
+    guarded = []
+
+    def guarded_empty(numel):
+        buf = ops.empty(numel + 2 * GUARD)
+        buf[:GUARD] = CANARY
+        buf[GUARD + numel:] = CANARY
+        guarded.append((buf, numel))
+        return buf[GUARD:GUARD + numel]
+
+    def check_guards(where):
+        for buf, numel in guarded:
+            assert bool((buf[:GUARD] == CANARY).all()) and bool((buf[GUARD + numel:] == CANARY).all()), "out-of-bounds store (%s)" % where
+
+    mats = [guarded_empty(C_ * plan.rows_per_rank) for _ in range(world)]          # rank g's [C][L/G]
     for rank in range(world):
         cols = plan.columns_of(rank)
         local = ops.to_tensor(vals[cols.start:cols.stop])
-        coeffs = ops.empty(len(cols) << log_n).view(len(cols), 1 << log_n)
-        scratch = ops.empty(len(cols) << (log_n + r))
+        coeffs = guarded_empty(len(cols) << log_n).view(len(cols), 1 << log_n)
+        scratch = guarded_empty(len(cols) << (log_n + r))
         shard_out = (C.c_void_p * world)(*[m.data_ptr() + plan.col_offsets[rank] * plan.rows_per_rank * 8 for m in mats])
         if rank % 2 == 0:
             check(lib().eng_lde_peer_dev(C.c_void_p(local.data_ptr()), len(cols), log_n, r, 1, plan.log_world,
@@ -323,6 +340,8 @@ def test_fused_exchange_stores_emulated_on_one_gpu(engine, oracle, world, log_n,
             check(lib().eng_lde_peer_host(ptrs, len(cols), log_n, r, 1, plan.log_world,
                                           C.c_void_p(coeffs.data_ptr()), C.c_void_p(scratch.data_ptr()), shard_out, rank))
         synchronize()
+        torch.cuda.synchronize()
+        check_guards("rank %d" % rank)
         assert (ops.to_numpy(coeffs) == ref.coeffs[cols.start:cols.stop]).all()
     caps = []
     for g in range(world):

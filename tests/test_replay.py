@@ -18,12 +18,16 @@ u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 
 @pytest.fixture(scope="module")
 def emu():
-    so = os.path.join(HERE, "emu", "libemu.so")
+    # EMU_ASAN=1 (tools/asan_replay.sh): the replay harness built with AddressSanitizer -- every load / store of the kernel
+    # bodies (tile staging, four-step index maps, leaf matrices of the row shards, digests) is bounds-checked on the CPU.
+    asan = os.environ.get("EMU_ASAN") == "1"
+    so = os.path.join(HERE, "emu", "libemu_asan.so" if asan else "libemu.so")
     src = os.path.join(HERE, "emu", "emu.cpp")
     csrc = os.path.join(HERE, "..", "eth-lc-plonky2_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+        flags = ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else ["-O2"]
+        subprocess.check_call(["/usr/bin/g++"] + flags + ["-std=c++17", "-fPIC", "-shared", "-o", so, src])
     L = C.CDLL(so)
     L.emu_poseidon_permute.argtypes = [u64p, u64p, C.c_size_t]
     L.emu_poseidon_permute_f64.argtypes = [u64p, u64p, C.c_size_t]
