@@ -10,6 +10,9 @@
  *   [DEP plonky2:fri/reduction_strategies.rs::ConstantArityBits]        
  * The prover here follows plonky2's COEFFICIENT-space route (Horner scan for divide_by_linear, coset FFT per fold
  * round); the CUDA engine computes the same objects in the evaluation domain, so agreement is a real cross-check.
+ * SECOND RESTATEMENT: tests/golden/plonk_restatement.py (pure Python: synthetic division in coefficient space, evaluation
+ * by Horner at every coset point instead of FFTs, Lagrange interpolation in the verifier's fold) reproduces this file's
+ * FriProof word for word, one reduction round included (tests/golden/plonk_proof.json).
  * Proof-of-work: plonky2 accepts any witness (rayon find_any); parity is defined on the SMALLEST valid witness.
  */
 #ifndef ORACLE_FRI_H

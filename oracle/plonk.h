@@ -2,6 +2,10 @@
  * restated, order-sensitive details cannot be checked against the absent source).  Self-consistency is established the
  * way the reference's tests do it (/root/reference/eth-lc-plonky2/src/unit_tests.rs:29-35): prove, then VERIFY with a
  * restatement of plonky2's verifier that re-evaluates every constraint at zeta over F_p^2.
+ * SECOND RESTATEMENT: tests/golden/plonk_restatement.py (pure Python, written from the published algorithm with different
+ * methods -- direct DFT sums, naive PoseidonGate rounds, level-by-level Merkle trees) proves the same circuits; its proofs
+ * (tests/golden/plonk_proof.json) equal this file's word for word, and its verifier accepts this file's proofs
+ * (tests/test_plonk_cpu.py::test_oracle_proof_equals_python_restatement).  Still not plonky2 output: the cap stays.
  *
  *   [DEP plonky2:plonk/prover.rs::{prove_with_partition_witness, wires_permutation_partial_products_and_zs,
  *        compute_quotient_polys}]                                            

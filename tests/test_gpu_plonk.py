@@ -175,3 +175,16 @@ def test_prove_2_18_verifies(engine, oracle):
     circ.verify(s["pi_hash"], proof)
     oc = oracle.Circuit(s["blob"])
     assert oc.verify(circ.constants_sigmas.merkle_tree.cap, s["pi_hash"], proof) == 0
+
+
+@pytest.mark.parametrize("k", [0, 1])
+def test_engine_proof_equals_python_restatement(engine, k):
+    """eng_prove against the pure-Python second restatement (tests/golden/plonk_proof.json), word for word."""
+    from test_plonk_cpu import _golden_plonk_cases, golden_plonk_circuit
+    E = engine
+    case = _golden_plonk_cases()[k]
+    s, gold = golden_plonk_circuit(case)
+    circ = E.Circuit.build(s)
+    assert [int(x) for x in circ.constants_sigmas.merkle_tree.cap.ravel()] == case["cs_cap"]
+    proof, _ = circ.prove(s["wires"], s["pi_hash"])
+    assert proof.shape == gold.shape and (proof == gold).all()

@@ -231,3 +231,63 @@ def test_circuit_descriptions_are_validated():
     b = blob.copy(); b[1] += np.uint64(1); rejected(b, "inconsistent")
     b = blob.copy(); b[20 + 1] = np.uint64(77); rejected(b, "selector index")
     rejected(blob, "does not parse")                                          # a well-formed circuit, a garbage proof
+
+
+# ---- second restatement (pure Python, tests/golden/plonk_restatement.py) pins oracle/plonk.h + oracle/fri.h ----
+def _golden_plonk_cases():
+    import json, os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "plonk_proof.json")) as f:
+        return json.load(f)["cases"]
+
+
+def golden_plonk_circuit(case):
+    import eth_lc_plonky2_b200 as E
+    s = E.synth_circuit(case["degree_bits"], seed=case["seed"])
+    s["blob"] = s["blob"].copy()
+    s["blob"][9], s["blob"][10] = case["pow_bits"], case["num_query_rounds"]
+    return s, np.array([int(x, 16) for x in case["proof"]], np.uint64)
+
+
+@pytest.mark.parametrize("k", [0, 1])
+def test_oracle_proof_equals_python_restatement(oracle, k):
+    """The C++ oracle (FFT butterflies, fast partial rounds, Horner division, fill_subtree) and the pure-Python restatement
+    (direct DFT sums, naive rounds, synthetic division in coefficient space, level-by-level trees) give the SAME proof, word
+    for word: caps, openings, FRI commit phase, grind, query openings.  Both verifiers and the product verifier accept it."""
+    import hashlib
+    import eth_lc_plonky2_b200 as E
+    case = _golden_plonk_cases()[k]
+    s, gold = golden_plonk_circuit(case)
+    circ = oracle.Circuit(s["blob"])
+    cs = oracle.Batch.from_values(np.concatenate([s["constants"], s["sigmas"]]), 3, 4)
+    assert [int(x) for x in np.array(cs.cap).ravel()] == case["cs_cap"]
+    betas, gammas = np.array(case["betas"], np.uint64), np.array(case["gammas"], np.uint64)
+    zs = circ.partial_products(s["wires"], s["sigmas"], betas, gammas)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).astype("<u8").tobytes()).hexdigest()
+    assert sha(zs) == case["sha256_zs_pp"]
+    wires = oracle.Batch.from_values(s["wires"], 3, 4)
+    zb = oracle.Batch.from_values(zs, 3, 4)
+    q = circ.quotient(cs, wires, zb, s["pi_hash"], betas, gammas, np.array(case["alphas"], np.uint64))
+    assert sha(q) == case["sha256_quotient_coeffs"]
+    proof = circ.prove(cs, s["wires"], s["sigmas"], s["pi_hash"])
+    assert proof.shape == gold.shape and (proof == gold).all()
+    assert circ.verify(cs.cap, s["pi_hash"], gold) == 0
+    E.verify(s["blob"], cs.cap, s["pi_hash"], gold)
+
+
+def test_python_verifier_accepts_oracle_proofs_and_rejects_tampering(oracle):
+    """The pure-Python verifier on a proof of the C++ oracle for ANOTHER witness (not the golden one)."""
+    import importlib.util, os
+    import eth_lc_plonky2_b200 as E
+    spec = importlib.util.spec_from_file_location("plonk_restatement", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "plonk_restatement.py"))
+    R = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(R)
+    s = E.synth_circuit(4, seed=99)
+    s["blob"] = s["blob"].copy(); s["blob"][9], s["blob"][10] = 4, 2
+    circ = oracle.Circuit(s["blob"])
+    cs = oracle.Batch.from_values(np.concatenate([s["constants"], s["sigmas"]]), 3, 4)
+    proof = [int(x) for x in circ.prove(cs, s["wires"], s["sigmas"], s["pi_hash"])]
+    blob, cap, pi = [int(x) for x in s["blob"]], [int(x) for x in np.array(cs.cap).ravel()], [int(x) for x in s["pi_hash"]]
+    assert R.verify(blob, cap, pi, proof) is None
+    bad = list(proof); bad[700] ^= 1
+    assert R.verify(blob, cap, pi, bad) is not None
+    assert R.verify(blob, cap, [pi[0] ^ 1] + pi[1:], proof) == "vanishing polynomial identity"
