@@ -45,6 +45,11 @@ GL_HD void plk_emit(PlkAcc &a, u64 term) {
     for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.sum[c] = gl_mul_add(a.apow[c * a.stride + a.t], term, a.sum[c]);
     a.t++;
 }
+// the same for a term whose index is not the running one
+GL_HD void plk_emit_at(PlkAcc &a, u32 t, u64 term) {
+#pragma unroll
+    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.sum[c] = gl_mul_add(a.apow[c * a.stride + t], term, a.sum[c]);
+}
 // host: fills the table for the given challenges
 static inline void plk_fill_apow(const u64 *alphas, u32 num_challenges, u32 stride, u64 *tab) {
     for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) {
@@ -267,19 +272,32 @@ GL_HD void quot_perm_point(const QuotParams &p, u64 t) {
     acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = 0;
     const u64 l0 = p.l0[pos];
     for (u32 c = 0; c < nch; c++) plk_emit(acc, gl_mul(l0, gl_sub(zs[c], 1)));
-    // partial-product checks, challenge-major.  beta * k_j * x = (beta x) * k_j: one product per wire and challenge
-    for (u32 c = 0; c < nch; c++) {
-        const u64 bx = gl_mul(p.beta[c], x);
-        for (u32 t = 0; t <= npp; t++) {
-            u64 prev = t == 0 ? zs[c] : zs[nch + c * npp + t - 1];
-            u64 next = t == npp ? zn[c] : zs[nch + c * npp + t];
-            u64 num = 1, den = 1;
-            for (u32 j = t * p.degree; j < (t + 1) * p.degree && j < p.num_routed; j++) {
-                u64 wv = w[j];
-                num = gl_mul(num, gl_add(gl_mul_add(bx, p.k_is[j], wv), p.gamma[c]));
-                den = gl_mul(den, gl_add(gl_mul_add(p.beta[c], sig[j], wv), p.gamma[c]));
+    // partial-product checks.  plonky2 orders the terms challenge-major (term index nch + c (npp + 1) + t); the loops run
+    // chunk-major so that every wire and sigma value is loaded ONCE for all challenges (ncu, round 2: the challenge-major
+    // loops read 23.0 GB for 13.5 GB of columns).  beta * k_j * x = (beta x) * k_j: one product per wire and challenge.
+    u64 bx[PLK_MAX_CHALLENGES];
+    for (u32 c = 0; c < nch; c++) bx[c] = gl_mul(p.beta[c], x);
+    for (u32 t = 0; t <= npp; t++) {
+        u64 num[PLK_MAX_CHALLENGES], den[PLK_MAX_CHALLENGES];
+#pragma unroll
+        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) num[c] = den[c] = 1;
+        for (u32 j = t * p.degree; j < (t + 1) * p.degree && j < p.num_routed; j++) {
+            const u64 wv = w[j], sv = sig[j], kj = p.k_is[j];
+#pragma unroll
+            for (int c = 0; c < PLK_MAX_CHALLENGES; c++) {
+                if ((u32)c < nch) {
+                    num[c] = gl_mul(num[c], gl_add(gl_mul_add(bx[c], kj, wv), p.gamma[c]));
+                    den[c] = gl_mul(den[c], gl_add(gl_mul_add(p.beta[c], sv, wv), p.gamma[c]));
+                }
             }
-            plk_emit(acc, gl_sub(gl_mul(prev, num), gl_mul(next, den)));
+        }
+#pragma unroll
+        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) {
+            if ((u32)c < nch) {
+                const u64 prev = t == 0 ? zs[c] : zs[nch + c * npp + t - 1];
+                const u64 next = t == npp ? zn[c] : zs[nch + c * npp + t];
+                plk_emit_at(acc, nch + c * (npp + 1) + t, gl_sub(gl_mul(prev, num[c]), gl_mul(next, den[c])));
+            }
         }
     }
     for (u32 c = 0; c < nch; c++) p.acc[(u64)c * p.count + t] = acc.sum[c];
