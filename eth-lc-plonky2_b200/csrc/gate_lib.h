@@ -1,6 +1,7 @@
 // Gate library: bytecode programs (gate_vm.h) of the plonky2 / plonky2_crypto gates whose constraint formulas are restated
 // in SURVEY.md A.8 and DESIGN.md 6.  Host code.  [DEP plonky2:gates/{constant,public_input,arithmetic_base,poseidon,base_sum,
-// arithmetic_extension,multiplication_extension,reducing,reducing_extension,random_access,exponentiation,poseidon_mds}.rs]
+// arithmetic_extension,multiplication_extension,reducing,reducing_extension,random_access,exponentiation,poseidon_mds,
+// coset_interpolation}.rs]
 // [DEP plonky2_crypto (plonky2_u32):gates/{arithmetic_u32,add_many_u32,subtraction_u32,range_check_u32,comparison}.rs]
 // Tier C of SURVEY.md Appendix A: wire layouts and constraint ORDER are recalled, not checked against the absent source;
 // with a Rust toolchain the programs are RECORDED from the gates' own eval_unfiltered_circuit instead and
@@ -13,7 +14,7 @@ enum PlkGateKind : u32 {
     PLK_NOOP = 0, PLK_CONSTANT = 1, PLK_PUBLIC_INPUT = 2, PLK_ARITHMETIC = 3, PLK_POSEIDON = 4, PLK_BASE_SUM = 5,
     PLK_ARITHMETIC_EXT = 6, PLK_MUL_EXT = 7, PLK_REDUCING = 8, PLK_REDUCING_EXT = 9, PLK_RANDOM_ACCESS = 10,
     PLK_EXPONENTIATION = 11, PLK_POSEIDON_MDS = 12, PLK_U32_ARITHMETIC = 13, PLK_U32_ADD_MANY = 14, PLK_U32_SUBTRACTION = 15,
-    PLK_U32_RANGE_CHECK = 16, PLK_COMPARISON = 17, PLK_NUM_KINDS = 18,
+    PLK_U32_RANGE_CHECK = 16, PLK_COMPARISON = 17, PLK_COSET_INTERPOLATION = 18, PLK_NUM_KINDS = 19,
     PLK_CUSTOM = 255   // no library builder: the program came over the ABI (recorded on the Rust side)
 };
 
@@ -27,6 +28,7 @@ static inline u32 plk_gate_degree(u32 kind, const u32 p[4]) {
         case PLK_ARITHMETIC: case PLK_ARITHMETIC_EXT: case PLK_MUL_EXT: return 3;
         case PLK_U32_ARITHMETIC: case PLK_U32_ADD_MANY: case PLK_U32_SUBTRACTION: case PLK_U32_RANGE_CHECK: case PLK_EXPONENTIATION: return 4;
         case PLK_COMPARISON: return 1u << ((p[0] + p[1] - 1) / p[1]);
+        case PLK_COSET_INTERPOLATION: return p[1];
         case PLK_RANDOM_ACCESS: return p[0] + 1;
         case PLK_POSEIDON: return 7;
     }
@@ -86,6 +88,38 @@ struct RandomAccessLayout {
     u32 num_routed() const { return (2 + vec_size()) * num_copies + num_extra; }
     u32 bit(u32 i, u32 c) const { return num_routed() + c * bits + i; }
 };
+
+struct CosetInterpLayout {   // CosetInterpolationGate { subgroup_bits, degree }, D = 2 (recursive FRI verifier: interpolate_coset)
+    u32 subgroup_bits, degree;
+    u32 num_points() const { return 1u << subgroup_bits; }
+    u32 num_intermediates() const { return (num_points() - 2) / (degree - 1); }
+    u32 shift() const { return 0; }
+    u32 value(u32 i) const { return 1 + 2 * i; }
+    u32 evaluation_point() const { return 1 + 2 * num_points(); }
+    u32 evaluation_value() const { return evaluation_point() + 2; }
+    u32 start_intermediates() const { return evaluation_value() + 2; }           // = number of routed wires
+    u32 intermediate_eval(u32 i) const { return start_intermediates() + 2 * i; }
+    u32 intermediate_prod(u32 i) const { return start_intermediates() + 2 * (num_intermediates() + i); }
+    u32 shifted_evaluation_point() const { return start_intermediates() + 4 * num_intermediates(); }
+    u32 num_wires() const { return shifted_evaluation_point() + 2; }
+    // chunk c of the interpolation covers points [first(c), last(c)): degree points first, then degree - 1 per intermediate
+    u32 first(u32 c) const { return c == 0 ? 0 : 1 + (degree - 1) * c; }
+    u32 last(u32 c) const { u32 e = c == 0 ? degree : first(c) + degree - 1; return e < num_points() ? e : num_points(); }
+};
+// two_adic_subgroup(bits) and its barycentric weights w_i = 1 / prod_{j != i} (x_i - x_j)   (host)
+static inline void plk_coset_domain(u32 bits, std::vector<u64> &domain, std::vector<u64> &weights) {
+    const u32 n = 1u << bits;
+    const u64 g = h_gl_root_of_unity((int)bits);
+    domain.assign(n, 1);
+    for (u32 i = 1; i < n; i++) domain[i] = h_gl_mul(domain[i - 1], g);
+    weights.assign(n, 1);
+    for (u32 i = 0; i < n; i++) {
+        u64 d = 1;
+        for (u32 j = 0; j < n; j++)
+            if (j != i) d = h_gl_mul(d, gl_canon(gl_sub(domain[i], domain[j])));
+        weights[i] = h_gl_inv(d);
+    }
+}
 
 // MDS layer on builder values: out[r] = sum_i in[(i + r) % 12] * CIRC[i] + (r == 0) * 8 * in[0]
 static inline void plk_build_mds(GvmBuilder &B, GvmVal (&s)[12]) {
@@ -364,6 +398,35 @@ static inline bool plk_build_gate(GvmBuilder &B, u32 kind, const u32 p[4], u32 n
         for (u32 i = 0; i <= cb; i++) B.emit(B.mul(bits[i], B.sub(one, bits[i])));
         B.emit(B.sub(B.add(B.imm(1ull << cb), B.wire(L.msd())), B.reduce_with_powers(bits, 2)));
         B.emit(B.sub(B.wire(L.result()), bits[cb]));
+        return true;
+    }
+    case PLK_COSET_INTERPOLATION: {
+        // p0 = subgroup_bits, p1 = degree.  shifted point * shift = evaluation point; barycentric interpolation of the 2^bits
+        // values over the subgroup at the shifted point, cut into chunks whose running (eval, product) pairs are wires:
+        //   eval' = eval * (z - x_i) + value_i * w_i * prod,   prod' = prod * (z - x_i)
+        CosetInterpLayout L = {p[0], p[1]};
+        if (L.subgroup_bits == 0 || L.subgroup_bits > 5 || L.degree < 2 || L.start_intermediates() > num_routed || L.num_wires() > num_wires) return false;
+        std::vector<u64> domain, weights;
+        plk_coset_domain(L.subgroup_bits, domain, weights);
+        const GvmVal shift = B.wire(L.shift());
+        const GvmExt z = X.wires(L.shifted_evaluation_point());
+        X.emit(X.sub(X.wires(L.evaluation_point()), X.scale(z, shift)));
+        GvmExt ev = {B.imm(0), B.imm(0)}, pr = {B.imm(1), B.imm(0)};
+        for (u32 c = 0; c <= L.num_intermediates(); c++) {
+            if (c > 0) {
+                const GvmExt ie = X.wires(L.intermediate_eval(c - 1)), ip = X.wires(L.intermediate_prod(c - 1));
+                X.emit(X.sub(ie, ev));
+                X.emit(X.sub(ip, pr));
+                ev = ie; pr = ip;
+            }
+            for (u32 i = L.first(c); i < L.last(c); i++) {
+                const GvmExt term = {B.sub(z.a, B.imm(domain[i])), z.b};
+                const GvmExt wv = X.scale(X.wires(L.value(i)), B.imm(weights[i]));
+                ev = X.add(X.mul(ev, term), X.mul(wv, pr));
+                pr = X.mul(pr, term);
+            }
+        }
+        X.emit(X.sub(X.wires(L.evaluation_value()), ev));
         return true;
     }
     }

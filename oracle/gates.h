@@ -5,7 +5,7 @@
  * (/root/reference/eth-lc-plonky2/src/merkle_tree_gadget.rs:37, targets.rs:198,317) and split_le_base::<2>
  * (/root/reference/eth-lc-plonky2/src/utils.rs:102-103) put into the eth-lc circuit.
  *   [DEP plonky2:gates/{base_sum,arithmetic_extension,multiplication_extension,reducing,reducing_extension,random_access,
- *        exponentiation,poseidon_mds}.rs]
+ *        exponentiation,poseidon_mds,coset_interpolation}.rs]
  *   [DEP plonky2_crypto @3f71378 (plonky2_u32 gates):gates/{arithmetic_u32,add_many_u32,subtraction_u32,range_check_u32,
  *        comparison}.rs]
  * Written as formulas over a generic field (O = OpsBase for the prover's points, OpsExt for the verifier's zeta); the engine
@@ -21,7 +21,8 @@
 enum {
     ORC_G_BASE_SUM = 5, ORC_G_ARITHMETIC_EXT = 6, ORC_G_MUL_EXT = 7, ORC_G_REDUCING = 8, ORC_G_REDUCING_EXT = 9,
     ORC_G_RANDOM_ACCESS = 10, ORC_G_EXPONENTIATION = 11, ORC_G_POSEIDON_MDS = 12, ORC_G_U32_ARITHMETIC = 13,
-    ORC_G_U32_ADD_MANY = 14, ORC_G_U32_SUBTRACTION = 15, ORC_G_U32_RANGE_CHECK = 16, ORC_G_COMPARISON = 17
+    ORC_G_U32_ADD_MANY = 14, ORC_G_U32_SUBTRACTION = 15, ORC_G_U32_RANGE_CHECK = 16, ORC_G_COMPARISON = 17,
+    ORC_G_COSET_INTERPOLATION = 18
 };
 
 /* an element of the extension algebra spread over two wires */
@@ -205,6 +206,47 @@ bool orc_eval_gate_ext(int kind, const int p[4], const typename O::T *w, const t
         for (int i = 0; i <= cb; i++) emit(O::mul(bits[i], O::sub(one, bits[i])));
         emit(O::sub(O::add(O::from(1ULL << cb), w[3]), orc_horner<O>(bits, 1, cb + 1, 2)));
         emit(O::sub(w[2], bits[cb]));
+        return true;
+    }
+    case ORC_G_COSET_INTERPOLATION: {
+        /* wire 0 = shift; values i at 1 + 2 i (2^bits of them); evaluation point, evaluation value; then the intermediate
+         * evals, the intermediate products, and the shifted evaluation point.  Interpolation over the subgroup <g> by the
+         * barycentric formula, evaluated chunk by chunk (degree points, then degree - 1 per intermediate pair). */
+        const int bits = p[0], deg = p[1], n = 1 << bits, ni = (n - 2) / (deg - 1);
+        const int w_point = 1 + 2 * n, w_value = w_point + 2, w_inter = w_value + 2, w_shifted = w_inter + 4 * ni;
+        std::vector<u64> xs(n), bw(n);
+        const u64 g = gl_root_of_unity(bits);
+        xs[0] = 1;
+        for (int i = 1; i < n; i++) xs[i] = gl_mul(xs[i - 1], g);
+        for (int i = 0; i < n; i++) {
+            u64 d = 1;
+            for (int j = 0; j < n; j++) if (j != i) d = gl_mul(d, gl_sub(xs[i], xs[j]));
+            bw[i] = gl_inv(d);
+        }
+        const OrcPair<O> z = orc_pair_at<O>(w, w_shifted), pt = orc_pair_at<O>(w, w_point);
+        emit(O::sub(pt.x, O::mul(z.x, w[0])));
+        emit(O::sub(pt.y, O::mul(z.y, w[0])));
+        OrcPair<O> ev = {O::from(0), O::from(0)}, pr = {O::from(1), O::from(0)};
+        int next = 0;
+        for (int c = 0; c <= ni; c++) {
+            if (c > 0) {
+                const OrcPair<O> ie = orc_pair_at<O>(w, w_inter + 2 * (c - 1)), ip = orc_pair_at<O>(w, w_inter + 2 * (ni + c - 1));
+                emit(O::sub(ie.x, ev.x)); emit(O::sub(ie.y, ev.y));
+                emit(O::sub(ip.x, pr.x)); emit(O::sub(ip.y, pr.y));
+                ev = ie; pr = ip;
+            }
+            const int count = c == 0 ? deg : deg - 1;
+            for (int k = 0; k < count && next < n; k++, next++) {
+                OrcPair<O> term = {O::sub(z.x, O::from(xs[next])), z.y};
+                OrcPair<O> v = orc_pair_at<O>(w, 1 + 2 * next);
+                OrcPair<O> wv = {O::scale(v.x, bw[next]), O::scale(v.y, bw[next])};
+                OrcPair<O> a = orc_pair_mul<O>(ev, term), b = orc_pair_mul<O>(wv, pr);
+                ev.x = O::add(a.x, b.x); ev.y = O::add(a.y, b.y);
+                pr = orc_pair_mul<O>(pr, term);
+            }
+        }
+        const OrcPair<O> out = orc_pair_at<O>(w, w_value);
+        emit(O::sub(out.x, ev.x)); emit(O::sub(out.y, ev.y));
         return true;
     }
     }

@@ -124,7 +124,7 @@ def test_all_gate_kinds_oracle_prove_then_verify(oracle, synth_v2, db):
 
 @pytest.mark.parametrize("native", [1, 0], ids=["poseidon_fp64", "poseidon_bytecode"])
 def test_all_gate_kinds_quotient_replay(emu, oracle, synth_v2, native):
-    """Bytecode (gate_lib.h) vs formulas (oracle/gates.h) for all 18 gate kinds, through the quotient kernels' bodies."""
+    """Bytecode (gate_lib.h) vs formulas (oracle/gates.h) for all 19 gate kinds, through the quotient kernels' bodies."""
     _quotient_replay(emu, oracle, synth_v2[5], 5, native)
 
 
