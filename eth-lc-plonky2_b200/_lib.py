@@ -83,6 +83,7 @@ _SIGNATURES = {
     "eng_blob_free": [_u64p],
     "eng_circuit_new": [_vp, _vp, C.POINTER(_vp), C.POINTER(_vp)],
     "eng_circuit_free": [_vp],
+    "eng_build_sigmas": [C.c_uint32, C.c_uint32, _vp, C.c_size_t, _vp],
     "eng_circuit_new_sharded": [_vp, C.POINTER(_vp), C.POINTER(_vp)],
     "eng_partial_products_dev": [_vp, C.POINTER(_vp), _vp, _vp, _vp],
     "eng_partial_products_from_dev": [_vp, _vp, _vp, _vp, _vp],

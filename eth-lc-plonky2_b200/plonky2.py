@@ -430,6 +430,15 @@ def synth_circuit_v2(degree_bits, seed=1, kinds_mask=ALL_GATES):
     return out
 
 
+def build_sigmas(degree_bits, num_routed, copies):
+    """eng_build_sigmas: sigma polynomial values [num_routed][n] from copy constraints [(row_a, col_a, row_b, col_b), ...]
+    (host code: the permutation half of CircuitBuilder::build())."""
+    c = np.ascontiguousarray(np.array(copies, dtype=np.uint32).reshape(-1, 4))
+    out = np.zeros((num_routed, 1 << degree_bits), np.uint64)
+    check(_lib.load().eng_build_sigmas(degree_bits, num_routed, c.ctypes.data_as(C.c_void_p), c.shape[0], ptr(out)))
+    return out
+
+
 def circuit_describe(header12, gates8, digest4):
     """eng_circuit_describe: version-2 description (with bytecode) of a circuit over library gates."""
     h, g_, d = host_u64(header12), host_u64(gates8).reshape(-1, 8), host_u64(digest4)

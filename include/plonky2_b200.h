@@ -218,6 +218,10 @@ typedef struct eng_circuit eng_circuit;
 eng_status eng_circuit_new(const uint64_t *blob, const eng_batch *constants_sigmas, const uint64_t *const *sigma_cols_host,
                            eng_circuit **out);
 eng_status eng_circuit_free(eng_circuit *c);
+/* Row f2, host half of build(): the sigma polynomials' values from the copy constraints (plonky2's Forest +
+ * WirePartition::get_sigma_polys).  copies: num_copies x (row_a, column_a, row_b, column_b) over routed wires; the wires
+ * of an equivalence class map cyclically onto each other in (row, column) order; sigmas_out [num_routed][2^degree_bits]. */
+eng_status eng_build_sigmas(uint32_t degree_bits, uint32_t num_routed, const uint32_t *copies, size_t num_copies, uint64_t *sigmas_out);
 typedef struct {
     uint32_t degree_bits, num_wires, num_routed_wires, num_constants /* selectors + gate constants */, num_selectors,
              num_challenges, quotient_degree_factor, num_partial_products, rate_bits, cap_height, num_gates,

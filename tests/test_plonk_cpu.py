@@ -291,3 +291,61 @@ def test_python_verifier_accepts_oracle_proofs_and_rejects_tampering(oracle):
     bad = list(proof); bad[700] ^= 1
     assert R.verify(blob, cap, pi, bad) is not None
     assert R.verify(blob, cap, [pi[0] ^ 1] + pi[1:], proof) == "vanishing polynomial identity"
+
+
+# ---- row f2, host half of build(): sigma polynomials from copy constraints ----
+def _sigma_value_table(db, num_routed):
+    n = 1 << db
+    g = pow(1753635133440165772, 1 << (32 - db), P_)
+    xs = [pow(g, i, P_) for i in range(n)]
+    return {(7 ** c % P_) * xs[r] % P_: (r, c) for c in range(num_routed) for r in range(n)}
+
+
+P_ = 0xFFFFFFFF00000001
+
+
+def test_build_sigmas_reproduces_the_synthetic_circuits(synth):
+    """The copy constraints read back out of the synthetic circuit's sigma columns give the same columns again."""
+    import eth_lc_plonky2_b200 as E
+    s = synth[5]
+    table = _sigma_value_table(5, 80)
+    copies = []
+    for c in range(80):
+        for r in range(32):
+            r2, c2 = table[int(s["sigmas"][c][r])]
+            if (r2, c2) > (r, c):
+                copies.append((r, c, r2, c2))
+    assert len(copies) > 50
+    assert (E.build_sigmas(5, 80, copies) == s["sigmas"]).all()
+    assert (E.build_sigmas(5, 80, []) == E.build_sigmas(5, 80, [(3, 4, 3, 4)])).all()          # identity permutation
+    with pytest.raises(E.EngineError):
+        E.build_sigmas(5, 80, [(0, 80, 1, 0)])
+
+
+def test_build_sigmas_against_a_python_union_find():
+    """Classes of any size (chains, stars, redundant constraints): every class is one cycle in (row, column) order, as
+    plonky2's WirePartition lists it; checked against a plain Python partition refinement."""
+    import eth_lc_plonky2_b200 as E
+    db, nr = 4, 7
+    n = 1 << db
+    rng = np.random.default_rng(5)
+    copies = [tuple(int(v) for v in (rng.integers(n), rng.integers(nr), rng.integers(n), rng.integers(nr))) for _ in range(60)]
+    copies += [(1, 1, 2, 2), (2, 2, 3, 3), (3, 3, 1, 1), (5, 0, 5, 0)]                      # a redundant triangle, a self-copy
+    cls = {(r, c): {(r, c)} for r in range(n) for c in range(nr)}
+    for ra, ca, rb, cb in copies:
+        a, b = cls[(ra, ca)], cls[(rb, cb)]
+        if a is not b:
+            a |= b
+            for w in b:
+                cls[w] = a
+    got = E.build_sigmas(db, nr, copies)
+    table = _sigma_value_table(db, nr)
+    seen = set()
+    for w, members in cls.items():
+        if id(members) in seen:
+            continue
+        seen.add(id(members))
+        order = sorted(members)
+        for i, (r, c) in enumerate(order):
+            assert table[int(got[c][r])] == order[(i + 1) % len(order)]
+    assert max(len(m) for m in cls.values()) > 3
