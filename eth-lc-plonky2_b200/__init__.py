@@ -5,7 +5,8 @@ this package is the thin host-side mirror of the plonky2 operator surface used b
 torch.distributed plumbing.  There is no CPU path.
 """
 from . import build as _build_mod
-from ._lib import (ENG_ERR_CUDA, ENG_ERR_INVALID, ENG_ERR_OOM, ENG_ERR_STATE, ENG_OK, EngineError, exported_symbols, init,
+from ._lib import (ENG_ERR_CUDA, ENG_ERR_INVALID, ENG_ERR_OOM, ENG_ERR_STATE, ENG_OK, EngineError, exported_symbols, host_register,
+                   host_unregister, init,
                    launch_count, load, measure_int_peak, release_cached, reserve, set_option, set_stream, so_path, synchronize)
 from .synthetic import splitmix_columns
 from .parallel import EngineOps, PeerExchange, ShardedPolynomialBatch, ShardedProver, ShardPlan, splice_initial_openings

@@ -44,6 +44,8 @@ _SIGNATURES = {
     "eng_launch_count": [_u64p],
     "eng_set_option": [C.c_char_p, C.c_int64],
     "eng_reserve": [C.c_size_t],
+    "eng_host_register": [_vp, C.c_size_t],
+    "eng_host_unregister": [_vp],
     "eng_measure_int_peak": [C.POINTER(C.c_double)],
     "eng_poseidon_permute": [_vp, _vp, C.c_size_t],
     "eng_hash_n": [_vp, C.c_size_t, C.c_size_t, C.c_int32, _vp],
@@ -178,6 +180,15 @@ def set_option(name, value):
 def reserve(num_bytes):
     """eng_reserve: grow the device memory pool ahead of the first proof."""
     check(lib().eng_reserve(int(num_bytes)))
+
+
+def host_register(array):
+    """eng_host_register: page-lock a numpy array (witness columns) for PCIe-speed column copies."""
+    check(lib().eng_host_register(C.c_void_p(array.ctypes.data), array.nbytes))
+
+
+def host_unregister(array):
+    check(lib().eng_host_unregister(C.c_void_p(array.ctypes.data)))
 
 
 def release_cached():

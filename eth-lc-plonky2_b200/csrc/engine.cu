@@ -680,6 +680,27 @@ eng_status eng_reserve(size_t bytes) {
     return ENG_OK;
 }
 
+// Page-locks a caller-owned host range (a witness column block, a Rust Vec) so that the column copies of
+// eng_batch_from_values / eng_prove / eng_lde_peer_host / eng_h2d_columns go straight to the copy engine at PCIe speed
+// instead of through the pinned bounce buffers (pageable memory: ~10 GB/s per process and host threads per copy).
+eng_status eng_host_register(const void *ptr, size_t bytes) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!ptr || !bytes) return fail(ENG_ERR_INVALID, "NULL / empty range");
+    cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return ENG_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ENG_ERR_CUDA, "cudaHostRegister of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
+    return ENG_OK;
+}
+eng_status eng_host_unregister(const void *ptr) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    ST(check_ready());
+    if (!ptr) return ENG_OK;
+    cudaError_t e = cudaHostUnregister(const_cast<void *>(ptr));
+    if (e != cudaSuccess) { cudaGetLastError(); if (e != cudaErrorHostMemoryNotRegistered) return fail(ENG_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+    return ENG_OK;
+}
+
 eng_status eng_synchronize(void) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     ST(check_ready());

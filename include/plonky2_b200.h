@@ -51,6 +51,10 @@ eng_status eng_release_cached(void);
  * the pool's growth buffer by buffer).  eng_circuit_new / eng_circuit_load call it with the footprint of one eng_prove
  * (option "reserve_for_proof", default 1); a prover can also call it early, while the host still builds the circuit. */
 eng_status eng_reserve(size_t bytes);
+/* Page-lock / release a caller-owned host range (witness columns): host-column entry points then copy at PCIe speed
+ * straight from it instead of through the engine's pinned bounce buffers. */
+eng_status eng_host_register(const void *ptr, size_t bytes);
+eng_status eng_host_unregister(const void *ptr);
 eng_status eng_launch_count(uint64_t *out);       /* kernels launched by the engine since eng_init */
 /* Engine options (A/B switches used by tests and profiles; defaults are the product path):
  *   "quot_native_poseidon" 1  PoseidonGate through the native FP64 evaluator (0: through its bytecode, like every other gate)

@@ -385,3 +385,17 @@ def test_maximum_sizes_properties(engine, oracle, log_n):
             assert int(row[c]) == ev(c, x)
         assert oracle.merkle_verify(row, k, cap, b.merkle_tree.prove(k))
     b.close()
+
+
+def test_registered_host_columns_take_the_direct_copy_path(engine, oracle):
+    """eng_host_register: page-locked caller memory is copied straight by the copy engine (no bounce buffers); same result."""
+    vals = oracle.splitmix_columns(9, 1 << 12)
+    o = oracle.Batch.from_values(vals, 3, 4)
+    engine.host_register(vals)
+    try:
+        b = engine.PolynomialBatch.from_values(list(vals), 3, False, 4)
+        assert (b.merkle_tree.cap == o.cap).all() and (b.polynomials == o.coeffs).all()
+        engine.host_register(vals)            # registering twice is not an error
+    finally:
+        engine.host_unregister(vals)
+    engine.host_unregister(vals)              # nor is releasing memory that is not registered
