@@ -183,11 +183,7 @@ static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs
         plan.push_back(ntt_make_launch(NTT_LDE_SINGLE, p));
         return true;
     }
-    // odd log_n: the STRIDED first pass takes the smaller half.  A 2^12-point strided tile needs 4 lanes (32-byte segments),
-    // i.e. 16 K elements = one CTA per SM; the contiguous last pass stages 2^12-point runs two per tile at two CTAs per SM
-    // (measured at 2^23 rows, the N = 8 weak-scaling shape: 41.8 ms with the 12 + 11 split against 34.4 ms predicted).
-    u32 lp = log_n / 2, lst = log_n - lp;
-    if (lst > NTT_MAX_LOGP || lst > p.log_shard_rows) { lp = ntt_split_first(log_n); lst = log_n - lp; }
+    u32 lp = ntt_split_first(log_n), lst = log_n - lp;
     if (lst > p.log_shard_rows) return false;  // a contiguous last-pass run must not straddle row shards
     auto w = ts.w2(log_n, false);
     auto s = ts.shift(log_n, rate_bits, lp);
