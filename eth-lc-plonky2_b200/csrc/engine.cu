@@ -80,6 +80,7 @@ struct Ctx {
     bool table_upload_failed = false;        // a twiddle / power table could not be placed on the device (reported by tables_ok)
     // eng_set_option
     int opt_native_poseidon = 1;             // quotient: PoseidonGate through the native FP64 evaluator (0: its bytecode)
+    int opt_peer_chunk_cols = 0;             // eng_lde_peer_dev: columns per iNTT + LDE chunk (0: the whole column shard at once)
     int opt_reserve = 1;                     // eng_circuit_new / eng_circuit_load grow the pool to one proof's footprint
     int opt_lde_group_mb = 0;                // LDE: megabytes of one (column, coset) group kept between the two passes (L2 residency)
 };
@@ -712,6 +713,7 @@ eng_status eng_set_option(const char *name, int64_t value) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!name) return fail(ENG_ERR_INVALID, "NULL option name");
     if (!strcmp(name, "quot_native_poseidon")) { g.opt_native_poseidon = value != 0; return ENG_OK; }
+    if (!strcmp(name, "lde_peer_chunk_cols")) { g.opt_peer_chunk_cols = value < 0 ? 0 : (int)value; return ENG_OK; }
     if (!strcmp(name, "reserve_for_proof")) { g.opt_reserve = value != 0; return ENG_OK; }
     if (!strcmp(name, "lde_group_mb")) { g.opt_lde_group_mb = value < 0 ? 0 : (int)value; return ENG_OK; }
     return fail(ENG_ERR_INVALID, "unknown option '%s'", name);
@@ -871,19 +873,30 @@ eng_status eng_lde_peer_dev(const uint64_t *src_dev, uint32_t num_polys, uint32_
     if (((u64)1 << log_row_shards) > NTT_MAX_SHARDS) return fail(ENG_ERR_INVALID, "more than %d row shards", NTT_MAX_SHARDS);
     for (u32 gi = 0; gi < (1u << log_row_shards); gi++)
         if (!shard_out[gi]) return fail(ENG_ERR_INVALID, "shard_out[%u] is NULL", gi);
-    const u64 n = (u64)1 << log_n;
-    std::vector<NttLaunch> plan;
-    if (is_values) {
-        if (!ntt_plan_intt(g.tables, src_dev, n, scratch_dev, n, coeffs_out_dev, n, num_polys, log_n, plan))
-            return fail(ENG_ERR_INVALID, "iNTT size unsupported");
-        ST(launch_plan(plan));
-    } else if (src_dev != coeffs_out_dev) {
+    const u64 n = (u64)1 << log_n, L = n << rate_bits, rows_per_shard = L >> log_row_shards;
+    const u32 G = 1u << log_row_shards;
+    // Column chunks (option lde_peer_chunk_cols, 0 = the whole shard at once): iNTT and LDE alternate chunk by chunk as in
+    // the host-column pipeline, which spreads the peer stores of the last pass over the whole transform instead of
+    // issuing all of them at the end (every rank of the box stores at the same time).
+    const u32 chunk = g.opt_peer_chunk_cols > 0 && (u32)g.opt_peer_chunk_cols < num_polys ? (u32)g.opt_peer_chunk_cols : num_polys;
+    if (!is_values && src_dev != coeffs_out_dev)
         CU(cudaMemcpyAsync(coeffs_out_dev, src_dev, (size_t)num_polys * n * sizeof(u64), cudaMemcpyDeviceToDevice, g.stream));
+    std::vector<NttLaunch> plan;
+    for (u32 c0 = 0; c0 < num_polys; c0 += chunk) {
+        const u32 cc = num_polys - c0 < chunk ? num_polys - c0 : chunk;
+        u64 *co = coeffs_out_dev + (size_t)c0 * n, *sc = scratch_dev + (size_t)c0 * L;
+        if (is_values) {
+            plan.clear();
+            if (!ntt_plan_intt(g.tables, src_dev + (size_t)c0 * n, n, sc, n, co, n, cc, log_n, plan)) return fail(ENG_ERR_INVALID, "iNTT size unsupported");
+            ST(launch_plan(plan));
+        }
+        u64 *so[NTT_MAX_SHARDS];
+        for (u32 gi = 0; gi < G; gi++) so[gi] = shard_out[gi] + (size_t)c0 * rows_per_shard;
+        plan.clear();
+        if (!ntt_plan_lde(g.tables, co, n, sc, cc, log_n, rate_bits, log_row_shards, plan, so, first_shard))
+            return fail(ENG_ERR_INVALID, "LDE shape unsupported (log_n=%u rate_bits=%u log_row_shards=%u)", log_n, rate_bits, log_row_shards);
+        ST(launch_plan(plan));
     }
-    plan.clear();
-    if (!ntt_plan_lde(g.tables, coeffs_out_dev, n, scratch_dev, num_polys, log_n, rate_bits, log_row_shards, plan, shard_out, first_shard))
-        return fail(ENG_ERR_INVALID, "LDE shape unsupported (log_n=%u rate_bits=%u log_row_shards=%u)", log_n, rate_bits, log_row_shards);
-    ST(launch_plan(plan));
     return ENG_OK;
 }
 

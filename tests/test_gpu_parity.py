@@ -324,6 +324,7 @@ def test_fused_exchange_stores_emulated_on_one_gpu(engine, oracle, world, log_n,
             assert bool((buf[:GUARD] == CANARY).all()) and bool((buf[GUARD + numel:] == CANARY).all()), "out-of-bounds store (%s)" % where
 
     mats = [guarded_empty(C_ * plan.rows_per_rank) for _ in range(world)]          # rank g's [C][L/G]
+    E.set_option("lde_peer_chunk_cols", 2 if world in (4, 16) else 0)              # chunked and unchunked device pipelines
     for rank in range(world):
         cols = plan.columns_of(rank)
         local = ops.to_tensor(vals[cols.start:cols.stop])
@@ -343,6 +344,7 @@ def test_fused_exchange_stores_emulated_on_one_gpu(engine, oracle, world, log_n,
         torch.cuda.synchronize()
         check_guards("rank %d" % rank)
         assert (ops.to_numpy(coeffs) == ref.coeffs[cols.start:cols.stop]).all()
+    E.set_option("lde_peer_chunk_cols", 0)
     caps = []
     for g in range(world):
         lo = g * plan.rows_per_rank

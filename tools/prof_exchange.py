@@ -54,8 +54,11 @@ def timed(name, fn, reps=4):
 lib = _lib.lib()
 timed("LDE -> local send buffer [G][C_r][L/G]", lambda: check(lib.eng_lde_dev(C.c_void_p(dev.data_ptr()), c_r, log_n, r, 1, plan.log_world,
                                                                                 C.c_void_p(coeffs.data_ptr()), C.c_void_p(send.data_ptr()))))
-timed("LDE with fused peer stores", lambda: check(lib.eng_lde_peer_dev(C.c_void_p(dev.data_ptr()), c_r, log_n, r, 1, plan.log_world,
-                                                                        C.c_void_p(coeffs.data_ptr()), C.c_void_p(send.data_ptr()), ex.shard_out, rank)))
+for chunk_cols in (0, 1, 2, 4, 8):
+    E.set_option("lde_peer_chunk_cols", chunk_cols)
+    timed("LDE with fused peer stores, chunk_cols=%d" % chunk_cols, lambda: check(lib.eng_lde_peer_dev(C.c_void_p(dev.data_ptr()), c_r, log_n, r, 1, plan.log_world,
+                                                                                                      C.c_void_p(coeffs.data_ptr()), C.c_void_p(send.data_ptr()), ex.shard_out, rank)))
+E.set_option("lde_peer_chunk_cols", 0)
 with torch.cuda.stream(stream):
     timed("NCCL all_to_all_single", lambda: dist.all_to_all_single(recv, send, output_split_sizes=plan.recv_splits(), input_split_sizes=plan.send_splits(rank)))
 
