@@ -80,7 +80,7 @@ struct Ctx {
     bool table_upload_failed = false;        // a twiddle / power table could not be placed on the device (reported by tables_ok)
     // eng_set_option
     int opt_native_poseidon = 1;             // quotient: PoseidonGate through the native FP64 evaluator (0: its bytecode)
-    int opt_peer_chunk_cols = 0;             // eng_lde_peer_dev: columns per iNTT + LDE chunk (0: the whole column shard at once)
+    int opt_peer_chunk_cols = 4;             // eng_lde_peer_dev: columns per iNTT + LDE chunk (0: the whole column shard at once)
     int opt_reserve = 1;                     // eng_circuit_new / eng_circuit_load grow the pool to one proof's footprint
     int opt_lde_group_mb = 0;                // LDE: megabytes of one (column, coset) group kept between the two passes (L2 residency)
 };

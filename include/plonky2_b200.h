@@ -61,6 +61,9 @@ eng_status eng_launch_count(uint64_t *out);       /* kernels launched by the eng
  *   "lde_group_mb"         0  megabytes of four-step intermediate a column group may hold between the two passes of a
  *                             transform so that the second pass reads it from the 126 MB L2 instead of HBM
  *                             (0: one launch per pass over the whole batch; measured in profiles/r02_ntt.md)
+ *   "lde_peer_chunk_cols"  4  eng_lde_peer_dev: iNTT + LDE alternate over chunks of this many columns, which spreads the peer
+ *                             stores over the whole transform (8 GPUs, 17 columns x 2^23 rows: 47.4 ms at once, 43.6 ms in
+ *                             chunks of 4; 0 = the whole column shard at once)
  *   "reserve_for_proof"    1  eng_circuit_new / eng_circuit_load grow the memory pool to one proof's footprint */
 eng_status eng_set_option(const char *name, int64_t value);
 
