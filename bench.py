@@ -478,8 +478,12 @@ def main():
         return cap
 
     # ---- device-resident arm ----
-    for _ in range(args.warmup):
-        step_device()
+    # warm-up on the SAME torch stream as the timed steps: torch's caching allocator keeps its blocks per stream, so a
+    # warm-up on the default stream would leave the first timed step to allocate its multi-GB scratch afresh (measured at
+    # N = 2: 460 ms for the first timed step against 147 ms for the others)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -489,8 +493,11 @@ def main():
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(args.steps):
+            t_step = time.perf_counter()
             for k, v in step_device().items():
                 stage_acc[k] = stage_acc.get(k, 0.0) + v
+            if os.environ.get("ENG_TRACE") and rank == 0:
+                print("rank 0: device step wall %.1f ms" % (1e3 * (time.perf_counter() - t_step)), flush=True)
         ev1.record(stream)
     barrier()
     launches = E.launch_count() - l0
@@ -498,8 +505,9 @@ def main():
     clocks = sampler.summary()
 
     # ---- end-to-end arm (host buffers through the C ABI) ----
-    for _ in range(max(1, min(args.warmup, 2))):
-        cap_e2e = step_e2e()
+    with torch.cuda.stream(stream):
+        for _ in range(max(1, min(args.warmup, 3))):
+            cap_e2e = step_e2e()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):

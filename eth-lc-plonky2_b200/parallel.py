@@ -238,6 +238,8 @@ class ShardedPolynomialBatch:
         when is_values is False).  Collective over `group` (torch.distributed).  With `exchange` (a PeerExchange of the
         same plan) the column->row exchange is fused into the LDE's last pass; the leaves land in leaf matrix `slot` of the
         exchange, which the returned batch refers to until a later call reuses that slot."""
+        import time as _time
+        t_enter = _time.perf_counter()
         if dist is None:
             import torch.distributed as dist
         if ops is None and not isinstance(local_values, (list, tuple)):
@@ -288,8 +290,8 @@ class ShardedPolynomialBatch:
             dist.all_gather(parts, local_cap, group=group)
             cap = np.concatenate([ops.to_numpy(p).reshape(-1, 4) for p in parts])
             if trace:
-                print("rank %d: alloc+barrier %.1f  lde %.1f  barrier %.1f  merkle+cap %.1f  gather %.1f ms" % (
-                    rank, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3), 1e3 * (time.perf_counter() - t4)), flush=True)
+                print("rank %d: enter %.1f  alloc+barrier %.1f  lde %.1f  barrier %.1f  merkle+cap %.1f  gather %.1f ms" % (
+                    rank, 1e3 * (t0 - t_enter), 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3), 1e3 * (time.perf_counter() - t4)), flush=True)
             return cls(plan, rank, coeffs, recv.view(plan.num_polys, plan.rows_per_rank), tree, cap, ops, exchange, slot)
         send = ops.empty(c_r * (n << plan.rate_bits))
         ops.lde(local_values, is_values, plan.log_n, plan.rate_bits, plan.log_world, coeffs, send)   # [G][C_r][L/G]
