@@ -22,7 +22,6 @@
 #include "ntt.cuh"
 #include "ntt_plan.h"
 #include "prover.cuh"
-#include "gate_lib.h"
 #include "plonk.cuh"
 #include <map>
 #include <sys/random.h>
@@ -79,6 +78,7 @@ struct Ctx {
     int stage_next = 0;
     bool table_upload_failed = false;        // a twiddle / power table could not be placed on the device (reported by tables_ok)
     // eng_set_option
+    int opt_native_gates = 1;                // quotient: library gates through the compiled evaluators (0: through their bytecode)
     int opt_native_poseidon = 1;             // quotient: PoseidonGate through the native FP64 evaluator (0: its bytecode)
     int opt_peer_chunk_cols = 4;             // eng_lde_peer_dev: columns per iNTT + LDE chunk (0: the whole column shard at once)
     int opt_reserve = 1;                     // eng_circuit_new / eng_circuit_load grow the pool to one proof's footprint
@@ -712,6 +712,7 @@ eng_status eng_synchronize(void) {
 eng_status eng_set_option(const char *name, int64_t value) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!name) return fail(ENG_ERR_INVALID, "NULL option name");
+    if (!strcmp(name, "quot_native_gates")) { g.opt_native_gates = value != 0; return ENG_OK; }
     if (!strcmp(name, "quot_native_poseidon")) { g.opt_native_poseidon = value != 0; return ENG_OK; }
     if (!strcmp(name, "lde_peer_chunk_cols")) { g.opt_peer_chunk_cols = value < 0 ? 0 : (int)value; return ENG_OK; }
     if (!strcmp(name, "reserve_for_proof")) { g.opt_reserve = value != 0; return ENG_OK; }

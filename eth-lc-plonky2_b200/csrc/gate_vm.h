@@ -122,6 +122,8 @@ struct GvmImmPool {
     }
 };
 struct GvmBuilder {
+    typedef GvmVal V;                          // gate_lib.h is written against a builder concept: V + the methods below
+    static constexpr bool kDirect = false;     // (QuotDirect in plonk.cuh is the other model: V = u64, evaluates in place)
     struct Ins { u32 op; u32 dst; GvmVal s[3]; int nsrc; };
     std::vector<Ins> ins;
     GvmImmPool &pool;
@@ -159,9 +161,9 @@ struct GvmBuilder {
         return r;
     }
     // sum_i v[i] * base^i  (reduce_with_powers), Horner from the top
-    GvmVal reduce_with_powers(const std::vector<GvmVal> &v, u64 base) {
-        GvmVal b = imm(base), acc = v.back();
-        for (size_t i = v.size() - 1; i-- > 0;) acc = mad(acc, b, v[i]);
+    GvmVal reduce_with_powers(const GvmVal *v, u32 n, u64 base) {
+        GvmVal b = imm(base), acc = v[n - 1];
+        for (u32 i = n - 1; i-- > 0;) acc = mad(acc, b, v[i]);
         return acc;
     }
     // prod_{k < count} (x - k)
@@ -205,18 +207,20 @@ struct GvmBuilder {
     }
 };
 
-// F_p^2 = F_p[X]/(X^2 - 7) on top of the builder (the recursion gates work on extension elements spread over D = 2 wires)
-struct GvmExt { GvmVal a, b; };
-struct GvmExtOps {
-    GvmBuilder &B;
-    explicit GvmExtOps(GvmBuilder &b) : B(b) {}
-    GvmExt wires(u32 first) { return GvmExt{B.wire(first), B.wire(first + 1)}; }
-    GvmExt add(GvmExt x, GvmExt y) { return GvmExt{B.add(x.a, y.a), B.add(x.b, y.b)}; }
-    GvmExt sub(GvmExt x, GvmExt y) { return GvmExt{B.sub(x.a, y.a), B.sub(x.b, y.b)}; }
-    GvmExt mul(GvmExt x, GvmExt y) {
-        GvmVal bb7 = B.mul(B.mul(x.b, y.b), B.imm(7));
-        return GvmExt{B.mad(x.a, y.a, bb7), B.mad(x.a, y.b, B.mul(x.b, y.a))};
+// F_p^2 = F_p[X]/(X^2 - 7) on top of a builder (the recursion gates work on extension elements spread over D = 2 wires)
+template <class BT> struct GvmExtT { typename BT::V a, b; };
+template <class BT> struct GvmExtOpsT {
+    typedef typename BT::V V;
+    typedef GvmExtT<BT> E;
+    BT &B;
+    GL_HD explicit GvmExtOpsT(BT &b) : B(b) {}
+    GL_HD E wires(u32 first) { return E{B.wire(first), B.wire(first + 1)}; }
+    GL_HD E add(E x, E y) { return E{B.add(x.a, y.a), B.add(x.b, y.b)}; }
+    GL_HD E sub(E x, E y) { return E{B.sub(x.a, y.a), B.sub(x.b, y.b)}; }
+    GL_HD E mul(E x, E y) {
+        V bb7 = B.mul(B.mul(x.b, y.b), B.imm(7));
+        return E{B.mad(x.a, y.a, bb7), B.mad(x.a, y.b, B.mul(x.b, y.a))};
     }
-    GvmExt scale(GvmExt x, GvmVal s) { return GvmExt{B.mul(x.a, s), B.mul(x.b, s)}; }
-    void emit(GvmExt x) { B.emit(x.a); B.emit(x.b); }
+    GL_HD E scale(E x, V s) { return E{B.mul(x.a, s), B.mul(x.b, s)}; }
+    GL_HD void emit(E x) { B.emit(x.a); B.emit(x.b); }
 };

@@ -22,6 +22,7 @@
 #pragma once
 #include "gl64.cuh"
 #include "gate_vm.h"
+#include "gate_lib.h"
 #include "poseidon.cuh"
 #include "prover.cuh"
 
@@ -198,7 +199,9 @@ GL_HD void plk_poseidon_gate_f64(const W &w, PlkAcc &acc) {
 struct PlkGateDev {            // one gate of the circuit as the kernels see it
     u32 prog_off, prog_len;    // words into QuotParams::prog
     u32 selector_index, group_start, group_end, row;   // row = index of the gate = the selector value that enables it
-    u32 num_constraints, native;                       // native != 0: evaluated by quot_poseidon_kernel, skipped by the interpreter
+    u32 num_constraints;
+    u32 native;                // 0: interpreted; 1: PoseidonGate through quot_poseidon_kernel; 2: compiled evaluator (quot_native_kernel)
+    u32 kind, p[4];            // library kind and parameters (native == 2: what plk_build_gate<QuotDirect> is run with)
 };
 
 // compute_filter(row, group, s, many_selectors)
@@ -233,7 +236,8 @@ struct QuotParams {
     const PlkGateDev *gates;       // device
     u32 num_gates;
     PlkGateDev poseidon;           // the natively evaluated gate (valid when has_poseidon)
-    u32 has_poseidon;
+    u32 has_poseidon;              // this launch sequence runs quot_poseidon_kernel: the interpreter skips native == 1 gates
+    u32 use_native_gates;          // ... and quot_native_kernel: the interpreter skips native == 2 gates
     const u64 *prog, *imm;         // device: programs, immediates (imm[0..4) = public_inputs_hash)
 };
 
@@ -331,14 +335,14 @@ struct QuotGvmEmit {
     PlkAcc *acc;
     GL_HD void operator()(u64 v) { plk_emit(*acc, v); }
 };
-GL_HD void quot_gates_point(const QuotParams &p, u64 t, bool include_native) {
+GL_HD void quot_gates_point(const QuotParams &p, u64 t) {
     PlkCols cs = {p.cs, p.stride, t};
     QuotGvmCtx cx = {{p.wires, p.stride, t}, {p.cs + (u64)p.num_selectors * p.stride, p.stride, t}, p.imm};
     u64 regs[GVM_NREG];
     u64 total[PLK_MAX_CHALLENGES] = {0, 0};
     for (u32 gi = 0; gi < p.num_gates; gi++) {
         const PlkGateDev g = p.gates[gi];
-        if (g.prog_len == 0 || (g.native && !include_native)) continue;
+        if (g.prog_len == 0 || (g.native == 1 && p.has_poseidon) || (g.native == 2 && p.use_native_gates)) continue;
         const u64 filter = plk_filter(g.row, g.group_start, g.group_end, cs[g.selector_index], p.num_selectors > 1);
         PlkAcc acc;
         for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
@@ -353,6 +357,76 @@ GL_HD void quot_gates_point(const QuotParams &p, u64 t, bool include_native) {
         *a = gl_add(*a, total[c]);
     }
 }
+
+// The compiled evaluators: gate_lib.h's formulas instantiated with a builder model that computes in place (V = u64).
+// Same source as the bytecode, so the two cannot drift; tests compare them gate by gate (CPU replay and GPU).
+struct QuotDirect {
+    typedef u64 V;
+    static constexpr bool kDirect = true;
+    PlkCols w, k;
+    const u64 *immv;
+    PlkAcc *acc;
+    GL_HD V wire(u32 i) const { return w[i]; }
+    GL_HD V constant(u32 i) const { return k[i]; }
+    GL_HD V pi(u32 i) const { return immv[i]; }
+    GL_HD V imm(u64 v) const { return v; }
+    GL_HD V add(V a, V b) const { return gl_add(a, b); }
+    GL_HD V sub(V a, V b) const { return gl_sub(a, b); }
+    GL_HD V mul(V a, V b) const { return gl_mul(a, b); }
+    GL_HD V mad(V a, V b, V c) const { return gl_mul_add(a, b, c); }
+    GL_HD V msub(V a, V b, V c) const { return gl_sub(gl_mul(a, b), c); }
+    GL_HD void emit(V v) const { plk_emit(*acc, v); }
+    GL_HD V pow(V x, u32 e) const {
+        V r = 1, b = x;
+        while (e) { if (e & 1) r = gl_mul(r, b); e >>= 1; if (e) b = gl_sqr(b); }
+        return r;
+    }
+    GL_HD V reduce_with_powers(const V *v, u32 n, u64 base) const {
+        V acc2 = v[n - 1];
+        for (u32 i = n - 1; i-- > 0;) acc2 = gl_mul_add(acc2, base, v[i]);
+        return acc2;
+    }
+    GL_HD V range_product(V x, u32 count) const {
+        V acc2 = x;
+        for (u32 j = 1; j < count; j++) acc2 = gl_mul(acc2, gl_sub(x, (u64)j));
+        return acc2;
+    }
+};
+// gates with native == 2 whose kind is in KIND_MASK: acc += filter * sum_t alpha^(first_gate_term + t) c_t.  The kind is
+// dispatched through compile-time constants so that a kernel contains the evaluators of ITS kinds only.
+template <u32 KIND_MASK>
+GL_HD void quot_native_point(const QuotParams &p, u64 t) {
+    const u32 kind_mask = KIND_MASK;
+    PlkCols cs = {p.cs, p.stride, t};
+    u64 total[PLK_MAX_CHALLENGES] = {0, 0};
+    for (u32 gi = 0; gi < p.num_gates; gi++) {
+        const PlkGateDev g = p.gates[gi];
+        if (g.native != 2 || !p.use_native_gates || !((kind_mask >> g.kind) & 1)) continue;
+        const u64 filter = plk_filter(g.row, g.group_start, g.group_end, cs[g.selector_index], p.num_selectors > 1);
+        PlkAcc acc;
+        for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
+        acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = p.first_gate_term;
+        QuotDirect ev = {{p.wires, p.stride, t}, {p.cs + (u64)p.num_selectors * p.stride, p.stride, t}, p.imm, &acc};
+#define PLK_NATIVE_CASE(K) if constexpr ((KIND_MASK >> (K)) & 1) { if (g.kind == (K)) plk_build_gate(ev, (u32)(K), g.p, p.num_wires, p.num_routed, p.num_gate_constants); }
+        PLK_NATIVE_CASE(PLK_CONSTANT) PLK_NATIVE_CASE(PLK_PUBLIC_INPUT) PLK_NATIVE_CASE(PLK_ARITHMETIC) PLK_NATIVE_CASE(PLK_BASE_SUM)
+        PLK_NATIVE_CASE(PLK_ARITHMETIC_EXT) PLK_NATIVE_CASE(PLK_MUL_EXT) PLK_NATIVE_CASE(PLK_REDUCING) PLK_NATIVE_CASE(PLK_REDUCING_EXT)
+        PLK_NATIVE_CASE(PLK_RANDOM_ACCESS) PLK_NATIVE_CASE(PLK_EXPONENTIATION) PLK_NATIVE_CASE(PLK_POSEIDON_MDS)
+        PLK_NATIVE_CASE(PLK_U32_ARITHMETIC) PLK_NATIVE_CASE(PLK_U32_ADD_MANY) PLK_NATIVE_CASE(PLK_U32_SUBTRACTION)
+        PLK_NATIVE_CASE(PLK_U32_RANGE_CHECK) PLK_NATIVE_CASE(PLK_COMPARISON)
+#undef PLK_NATIVE_CASE
+#pragma unroll
+        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) total[c] = gl_mul_add(filter, acc.sum[c], total[c]);
+    }
+    for (u32 c = 0; c < p.num_challenges; c++) {
+        u64 *a = &p.acc[(u64)c * p.count + t];
+        *a = gl_add(*a, total[c]);
+    }
+}
+// the compiled evaluators are spread over three kernels by code size (arithmetic + recursion / lookups + exponentiation / u32)
+#define PLK_NATIVE_GROUP_A ((1u << PLK_CONSTANT) | (1u << PLK_PUBLIC_INPUT) | (1u << PLK_ARITHMETIC) | (1u << PLK_BASE_SUM) | (1u << PLK_ARITHMETIC_EXT) | (1u << PLK_MUL_EXT) | (1u << PLK_REDUCING) | (1u << PLK_REDUCING_EXT))
+#define PLK_NATIVE_GROUP_B ((1u << PLK_RANDOM_ACCESS) | (1u << PLK_EXPONENTIATION) | (1u << PLK_POSEIDON_MDS))
+#define PLK_NATIVE_GROUP_C ((1u << PLK_U32_ARITHMETIC) | (1u << PLK_U32_ADD_MANY) | (1u << PLK_U32_SUBTRACTION) | (1u << PLK_U32_RANGE_CHECK) | (1u << PLK_COMPARISON))
+#define PLK_NATIVE_KINDS (PLK_NATIVE_GROUP_A | PLK_NATIVE_GROUP_B | PLK_NATIVE_GROUP_C)
 
 // * 1 / Z_H(x); position -> natural index
 GL_HD void quot_finish_point(const QuotParams &p, u64 t) {
@@ -488,10 +562,16 @@ __global__ void __launch_bounds__(128) quot_poseidon_kernel(QuotParams p) {
     if (t >= p.count) return;
     quot_poseidon_point(p, t);
 }
-__global__ void __launch_bounds__(128) quot_gates_kernel(QuotParams p, int include_native) {
+__global__ void __launch_bounds__(128) quot_gates_kernel(QuotParams p) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.count) return;
-    quot_gates_point(p, t, include_native != 0);
+    quot_gates_point(p, t);
+}
+template <u32 KIND_MASK>
+__global__ void __launch_bounds__(128) quot_native_kernel(QuotParams p) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.count) return;
+    quot_native_point<KIND_MASK>(p, t);
 }
 __global__ void __launch_bounds__(256) quot_unshard_kernel(const u64 *in, u64 *out, u32 log_lq, u32 log_shards, u32 nch) {
     const u64 pos = (u64)blockIdx.x * blockDim.x + threadIdx.x;

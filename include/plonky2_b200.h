@@ -57,6 +57,8 @@ eng_status eng_host_register(const void *ptr, size_t bytes);
 eng_status eng_host_unregister(const void *ptr);
 eng_status eng_launch_count(uint64_t *out);       /* kernels launched by the engine since eng_init */
 /* Engine options (A/B switches used by tests and profiles; defaults are the product path):
+ *   "quot_native_gates"    1  library gates whose program is gate_lib.h's run through the compiled evaluators (the same source
+ *                             instantiated for the device) instead of the bytecode interpreter (0: interpret everything)
  *   "quot_native_poseidon" 1  PoseidonGate through the native FP64 evaluator (0: through its bytecode, like every other gate)
  *   "lde_group_mb"         0  megabytes of four-step intermediate a column group may hold between the two passes of a
  *                             transform so that the second pass reads it from the 126 MB L2 instead of HBM

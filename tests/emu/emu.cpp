@@ -21,7 +21,6 @@ static double g_l3_maxabs = 0.0;   // largest lazy 96-bit magnitude built by ntt
 #include "../../eth-lc-plonky2_b200/csrc/ntt.cuh"
 #include "../../eth-lc-plonky2_b200/csrc/ntt_plan.h"
 #include "../../eth-lc-plonky2_b200/csrc/plonk.cuh"
-#include "../../eth-lc-plonky2_b200/csrc/gate_lib.h"
 
 static std::vector<std::unique_ptr<std::vector<u64>>> g_tables;
 
@@ -211,6 +210,8 @@ static bool emu_parse_circuit(const u64 *b, EmuCircuit &C) {
         memset(&g, 0, sizeof(g));
         g.prog_off = (u32)C.prog.size(); g.prog_len = (u32)program.size();
         g.selector_index = (u32)e[1]; g.group_start = (u32)e[2]; g.group_end = (u32)e[3]; g.row = i;
+        g.kind = kind;
+        for (int k = 0; k < 4; k++) g.p[k] = p[k];
         C.prog.insert(C.prog.end(), program.begin(), program.end());
         C.gates.push_back(g);
         if (kind == PLK_POSEIDON && C.poseidon_index < 0) C.poseidon_index = (int)i;
@@ -259,8 +260,11 @@ int emu_quotient_values_sharded(const u64 *blob, const u64 *cs_lde, const u64 *w
     plk_fill_apow(alpha_c, nch, q.apow_stride, apow_tab.data());
     q.apow = apow_tab.data(); q.acc = acc.data(); q.l0 = l0.data();
     for (int i = 0; i < 4; i++) C.imm[i] = gl_canon(pi_hash[i]);
-    const bool nat = native && C.poseidon_index >= 0;
-    for (size_t i = 0; i < C.gates.size(); i++) C.gates[i].native = nat && (int)i == C.poseidon_index;
+    // native bit 0: PoseidonGate through the FP64 evaluator; bit 1: the library gates through the compiled evaluators
+    const bool nat = (native & 1) && C.poseidon_index >= 0, compiled = (native & 2) != 0;
+    for (size_t i = 0; i < C.gates.size(); i++)
+        C.gates[i].native = (int)i == C.poseidon_index ? 1 : (C.gates[i].kind < 32 && ((PLK_NATIVE_KINDS >> C.gates[i].kind) & 1)) ? 2 : 0;
+    q.use_native_gates = compiled;
     q.gates = C.gates.data(); q.num_gates = (u32)C.gates.size(); q.prog = C.prog.data(); q.imm = C.imm.data();
     q.has_poseidon = nat;
     if (C.poseidon_index >= 0) q.poseidon = C.gates[C.poseidon_index];
@@ -275,7 +279,8 @@ int emu_quotient_values_sharded(const u64 *blob, const u64 *cs_lde, const u64 *w
     if (log_shards == 0) {
         for (u64 pos = 0; pos < Lq; pos++) quot_perm_point(q, pos);
         if (nat) for (u64 pos = 0; pos < Lq; pos++) quot_poseidon_point(q, pos);
-        for (u64 pos = 0; pos < Lq; pos++) quot_gates_point(q, pos, !nat);
+        if (compiled) for (u64 pos = 0; pos < Lq; pos++) quot_native_point<PLK_NATIVE_KINDS>(q, pos);
+        for (u64 pos = 0; pos < Lq; pos++) quot_gates_point(q, pos);
         for (u64 pos = 0; pos < Lq; pos++) quot_finish_point(q, pos);
         g_tables.clear();
         return 0;
@@ -297,7 +302,8 @@ int emu_quotient_values_sharded(const u64 *blob, const u64 *cs_lde, const u64 *w
         s2.by_position = 1; s2.acc = sacc.data(); s2.out = &gathered[(size_t)gsh * nch * count];
         for (u64 t = 0; t < count; t++) quot_perm_point(s2, t);
         if (nat) for (u64 t = 0; t < count; t++) quot_poseidon_point(s2, t);
-        for (u64 t = 0; t < count; t++) quot_gates_point(s2, t, !nat);
+        if (compiled) for (u64 t = 0; t < count; t++) quot_native_point<PLK_NATIVE_KINDS>(s2, t);
+        for (u64 t = 0; t < count; t++) quot_gates_point(s2, t);
         for (u64 t = 0; t < count; t++) quot_finish_point(s2, t);
     }
     for (u64 pos = 0; pos < Lq; pos++) quot_unshard_point(gathered.data(), out, log_lq, log_shards, nch, pos);

@@ -86,7 +86,8 @@ def test_all_gate_kinds_prove_matches_oracle_and_verifies(engine, oracle, db):
 
 @pytest.mark.parametrize("which,db", [("v1", 7), ("v2", 7)])
 def test_native_poseidon_gate_equals_bytecode(engine, which, db):
-    """quot_poseidon_kernel (FP64 permutation) against the interpreter running PoseidonGate's bytecode."""
+    """quot_poseidon_kernel (FP64 permutation) and quot_native_kernel (the compiled library evaluators) against the
+    interpreter running the same gates' bytecode: all four combinations give the same quotient polynomials."""
     E = engine
     s = E.synth_circuit(db, seed=5) if which == "v1" else E.synth_circuit_v2(db, seed=5)
     circ = E.Circuit.build(s)
@@ -95,12 +96,16 @@ def test_native_poseidon_gate_equals_bytecode(engine, which, db):
     wires = E.PolynomialBatch.from_values(list(s["wires"]), 3, False, 4)
     zs = E.PolynomialBatch.from_values(list(circ.partial_products(s["wires"], betas, gammas)), 3, False, 4)
     try:
-        E.set_option("quot_native_poseidon", 1)
-        a = circ.quotient(wires, zs, s["pi_hash"], betas, gammas, alphas).polynomials
-        E.set_option("quot_native_poseidon", 0)
-        b = circ.quotient(wires, zs, s["pi_hash"], betas, gammas, alphas).polynomials
+        outs = []
+        for native_poseidon, native_gates in ((1, 1), (1, 0), (0, 1), (0, 0)):    # compiled / FP64 evaluators vs the interpreter
+            E.set_option("quot_native_poseidon", native_poseidon)
+            E.set_option("quot_native_gates", native_gates)
+            outs.append(circ.quotient(wires, zs, s["pi_hash"], betas, gammas, alphas).polynomials)
     finally:
         E.set_option("quot_native_poseidon", 1)
+        E.set_option("quot_native_gates", 1)
+    a, b = outs[0], outs[3]
+    assert all((o == a).all() for o in outs)
     assert (a == b).all()
     assert (a[:, -1] != 0).any()      # degree really reaches 8n - 1 chunks (the quotient is not trivially zero)
 

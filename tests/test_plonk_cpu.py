@@ -76,7 +76,7 @@ def _quotient_replay(emu, oracle, s, db, native):
         assert (co.reshape(8, -1) == ref[8 * c:8 * c + 8]).all()
 
 
-@pytest.mark.parametrize("native", [1, 0], ids=["poseidon_fp64", "poseidon_bytecode"])
+@pytest.mark.parametrize("native", [3, 1, 0], ids=["compiled+poseidon_fp64", "bytecode+poseidon_fp64", "all_bytecode"])
 @pytest.mark.parametrize("db", [3, 5])
 def test_quotient_point_replay(emu, oracle, synth, db, native):
     """The four quotient kernels' bodies (PoseidonGate through the FP64 evaluator or through its bytecode; the other gates
@@ -122,9 +122,10 @@ def test_all_gate_kinds_oracle_prove_then_verify(oracle, synth_v2, db):
     assert circ.verify(cs.cap, s["pi_hash"], proof) == 0
 
 
-@pytest.mark.parametrize("native", [1, 0], ids=["poseidon_fp64", "poseidon_bytecode"])
+@pytest.mark.parametrize("native", [3, 2, 1, 0], ids=["compiled+poseidon_fp64", "compiled+poseidon_bytecode", "bytecode+poseidon_fp64", "all_bytecode"])
 def test_all_gate_kinds_quotient_replay(emu, oracle, synth_v2, native):
-    """Bytecode (gate_lib.h) vs formulas (oracle/gates.h) for all 19 gate kinds, through the quotient kernels' bodies."""
+    """Bytecode (gate_lib.h through the interpreter), the COMPILED evaluators (the same gate_lib.h source instantiated with the
+    in-place builder model) and formulas (oracle/gates.h) for all 19 gate kinds, through the quotient kernels' bodies."""
     _quotient_replay(emu, oracle, synth_v2[5], 5, native)
 
 
