@@ -220,7 +220,7 @@ def proof_section(E, log_n, reps=4, all_gates=False):
     return {"metric": "synthetic_proof_wall_time", "value": best, "unit": "s", "all_runs_s": walls, "witness_memory": "page-locked (eng_host_register)" if pinned else "pageable",
             "higher_is_better": False, "log_rows": log_n,
             "config": "circuit-shaped synthetic proof, 2^%d rows x 135 wires, %s, standard_recursion_config" % (
-                log_n, "19 gate kinds (core + recursion + u32, bytecode)" if all_gates else "5 core gates"),
+                log_n, "19 gate kinds (core + recursion + u32; bytecode description, library gates compiled)" if all_gates else "5 core gates"),
             "build_constants_sigmas_commit_s": build_s, "first_call_s": build_s + walls[0],
             "first_call_note": "Circuit.build (constants||sigmas commit + memory-pool growth for one proof) + the first eng_prove of the process",
             "stage_ms": stages, "proof_u64_words": int(proof.size), "proof_sha256": hashlib.sha256(proof.tobytes()).hexdigest(),
