@@ -10,7 +10,7 @@ from ._lib import (ENG_ERR_CUDA, ENG_ERR_INVALID, ENG_ERR_OOM, ENG_ERR_STATE, EN
                    launch_count, load, measure_int_peak, release_cached, reserve, set_option, set_stream, so_path, synchronize)
 from .synthetic import splitmix_columns
 from .parallel import EngineOps, PeerExchange, ShardedPolynomialBatch, ShardedProver, ShardPlan, splice_initial_openings
-from .plonky2 import ALL_GATES, GATE_KINDS, Circuit, build_sigmas, circuit_describe, proof_from_bytes, proof_to_bytes, synth_circuit, synth_circuit_v2, verify
+from .plonky2 import ALL_GATES, GATE_KINDS, Circuit, build_sigmas, circuit_describe, proof_from_bytes, proof_to_bytes, public_inputs_hash, synth_circuit, synth_circuit_v2, verify
 from .plonky2 import Challenger, FriInstanceInfo, FriParams, FriProof, reduction_arity_bits
 from .plonky2 import SALT_SIZE, MerkleTree, PolynomialBatch, PoseidonHash, poseidon
 

@@ -104,6 +104,7 @@ _SIGNATURES = {
     "eng_proof_to_bytes": [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)],
     "eng_proof_from_bytes": [_vp, _vp, C.c_size_t, C.POINTER(_u64p), C.POINTER(C.c_size_t), C.POINTER(_u64p), C.POINTER(C.c_size_t)],
     "eng_bytes_free": [C.POINTER(C.c_uint8)],
+    "eng_public_inputs_hash": [_vp, C.c_size_t, _vp],
     "eng_synth_circuit_v2": [C.c_uint32, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint32), C.POINTER(_u64p), C.POINTER(C.c_size_t)],
     "eng_partial_products": [_vp, C.POINTER(_vp), _vp, _vp, _vp],
     "eng_quotient": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)],

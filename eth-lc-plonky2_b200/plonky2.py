@@ -460,6 +460,14 @@ def verify(circuit_blob, constants_sigmas_cap, public_inputs_hash, proof_blob):
     check(_lib.load().eng_verify(ptr(b), ptr(cap), ptr(pi), ptr(pr), pr.size))
 
 
+def public_inputs_hash(public_inputs):
+    """PoseidonHash::hash_no_pad(public_inputs) -> the 4 words Circuit.prove / verify take (host code)."""
+    pis = host_u64(list(public_inputs))
+    out = np.zeros(4, np.uint64)
+    check(_lib.load().eng_public_inputs_hash(ptr(pis), pis.size, ptr(out)))
+    return out
+
+
 def proof_to_bytes(circuit_blob, proof_blob, public_inputs=()):
     """ProofWithPublicInputs::to_bytes (plonky2's wire format as restated; see include/plonky2_b200.h)."""
     b, pr, pis = host_u64(circuit_blob), host_u64(proof_blob), host_u64(list(public_inputs))

@@ -321,6 +321,8 @@ eng_status eng_fri_prove_from_layer_dev(const uint64_t *layer0_dev, eng_challeng
  * the failing check in eng_last_error (the Rust shim turns that into verify()'s Err). */
 eng_status eng_verify(const uint64_t *circuit_blob, const uint64_t *constants_sigmas_cap, const uint64_t *public_inputs_hash,
                       const uint64_t *proof_blob, size_t proof_len);
+/* public_inputs_hash = PoseidonHash::hash_no_pad(public_inputs) (host code): the 4 words eng_prove / eng_verify take. */
+eng_status eng_public_inputs_hash(const uint64_t *public_inputs, size_t num_public_inputs, uint64_t out[4]);
 /* plonky2's wire format as restated (to be re-checked against the source): little-endian
  * canonical u64 per field element, caps / openings / FRI layers in struct order without length prefixes, one byte of
  * sibling count in front of every Merkle proof, the public inputs last.  *bytes_out: malloc'ed (eng_bytes_free). */

@@ -350,3 +350,11 @@ def test_build_sigmas_against_a_python_union_find():
         for i, (r, c) in enumerate(order):
             assert table[int(got[c][r])] == order[(i + 1) % len(order)]
     assert max(len(m) for m in cls.values()) > 3
+
+
+def test_public_inputs_hash_is_hash_no_pad(oracle):
+    import eth_lc_plonky2_b200 as E
+    for n in (0, 1, 8, 16, 19):
+        pis = [(i * 0x9E3779B97F4A7C15 + 5) % (2**64) for i in range(n)]
+        want = oracle.hash_no_pad(np.array(pis, np.uint64)) if n else np.zeros(4, np.uint64)
+        assert (E.public_inputs_hash(pis) == want).all()
