@@ -660,6 +660,10 @@ eng_status eng_release_cached(void) {
 eng_status eng_reserve(size_t bytes) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     ST(check_ready());
+    // blocks parked in the engine's exact-size cache count as "used" for the pool: hand them back first, so that they are
+    // part of the idle memory the reservation is measured against (and usable for the new shapes)
+    cache_flush();
+    CU(cudaStreamSynchronize(g.stream));
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, g.device));
     uint64_t reserved = 0, used = 0;
