@@ -194,7 +194,7 @@ eng_status eng_batch_eval_ext(const eng_batch *b, const uint64_t z[2], uint64_t 
  * params (FriParams): [degree_bits, rate_bits, cap_height, proof_of_work_bits, num_query_rounds,
  *   reduction_arity_bits.len(), reduction_arity_bits...]  (arity 16 only: ConstantArityBits(4, _)).
  * The challenger must be in the state right after observing the openings; it is advanced exactly as plonky2's.
- * Output (FriProof), a malloc'ed flat u64 array released with eng_blob_free (NOT plonky2's wire format, row f4):
+ * Output (FriProof), a malloc'ed flat u64 array released with eng_blob_free (plonky2's byte format: eng_proof_to_bytes):
  *   [R] R x { [len] cap } | [F] F x (a, b) final_poly | pow_witness |
  *   [Q] Q x { [O] O x { [leaf_len] leaf | [path_len] path x 4 } | [R] R x { [arity] evals x 2 | [path_len] path x 4 } }
  * pow_witness is the SMALLEST valid witness (plonky2's rayon find_any returns an arbitrary one). */
@@ -218,7 +218,9 @@ eng_status eng_blob_free(uint64_t *blob);
  *   2 PublicInput, 3 Arithmetic{p0 ops}, 4 Poseidon, 5 BaseSum<p0>{p1 limbs}, 6 ArithmeticExtension{p0}, 7 MulExtension{p0},
  *   8 Reducing{p0 coeffs}, 9 ReducingExtension{p0}, 10 RandomAccess{p0 bits, p1 copies, p2 extra constants},
  *   11 Exponentiation{p0 bits}, 12 PoseidonMds, 13 U32Arithmetic{p0}, 14 U32AddMany{p0 addends, p1 ops}, 15 U32Subtraction{p0},
- *   16 U32RangeCheck{p0 limbs}, 17 Comparison{p0 bits, p1 chunks}; 255 = custom (the program is mandatory).
+ *   16 U32RangeCheck{p0 limbs}, 17 Comparison{p0 bits, p1 chunks}, 18 CosetInterpolation{p0 subgroup bits, p1 degree};
+ *   255 = custom (the program is mandatory).  A library gate whose program is the library's own runs through the evaluators
+ *   compiled from the same source (option quot_native_gates); anything else through the bytecode interpreter.
  * Version 1 (the five core gates, kept for round-1 callers): the 12 header words, (kind, selector_index, group.start,
  *   group.end) x num_gates, circuit_digest x 4.
  * constants_sigmas: the batch committed by build() (selectors, gate constants, sigmas -- in that column order);
