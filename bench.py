@@ -184,7 +184,7 @@ def proof_section(E, log_n, reps=4, all_gates=False):
     plonky2's Rust front-end), so this is the circuit-SHAPED synthetic proof of SURVEY.md 8(d): 135 wires, 80 routed,
     selectors + 2 constants + 80 sigmas, standard_recursion_config (rate_bits 3, cap_height 4, 16-bit grind, 28 queries),
     witness on the host, everything after witness generation on the GPU through eng_prove.  Gate set: the five core gates
-    (half the rows PoseidonGate), or with all_gates the 19 gate kinds of gate_lib.h (recursion + plonky2_crypto u32 gates,
+    (half the rows PoseidonGate), or with all_gates the 22 gate kinds of gate_lib.h (recursion + plonky2_crypto u32 gates,
     evaluated from bytecode) -- the gate mix of the real circuit.  Wall clock around the call with host wire columns (H2D
     inside).  Every proof is verified (product verifier + the oracle's restatement of plonky2's)."""
     import hashlib
@@ -220,7 +220,7 @@ def proof_section(E, log_n, reps=4, all_gates=False):
     return {"metric": "synthetic_proof_wall_time", "value": best, "unit": "s", "all_runs_s": walls, "witness_memory": "page-locked (eng_host_register)" if pinned else "pageable",
             "higher_is_better": False, "log_rows": log_n,
             "config": "circuit-shaped synthetic proof, 2^%d rows x 135 wires, %s, standard_recursion_config" % (
-                log_n, "19 gate kinds (core + recursion + u32; bytecode description, library gates compiled)" if all_gates else "5 core gates"),
+                log_n, "22 gate kinds (core + recursion + u32; bytecode description, library gates compiled)" if all_gates else "5 core gates"),
             "build_constants_sigmas_commit_s": build_s, "first_call_s": build_s + walls[0],
             "first_call_note": "Circuit.build (constants||sigmas commit + memory-pool growth for one proof) + the first eng_prove of the process",
             "stage_ms": stages, "proof_u64_words": int(proof.size), "proof_sha256": hashlib.sha256(proof.tobytes()).hexdigest(),
@@ -393,7 +393,7 @@ def main():
     ap.add_argument("--dist-proof-full-log-n", type=int, default=22, help="N > 1: the eth-lc-sized proof (2^22 rows) over all ranks; 0 = skip")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1 commit: weak = 2^log_n rows PER GPU (default, the driver's scaling run); strong = 2^log_n rows in total")
-    ap.add_argument("--all-gates-proof-log-n", type=int, default=20, help="N = 1: rows (log2) of the synthetic proof over all 19 gate kinds; 0 = skip")
+    ap.add_argument("--all-gates-proof-log-n", type=int, default=20, help="N = 1: rows (log2) of the synthetic proof over all 22 gate kinds; 0 = skip")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: column->row exchange fused into the LDE's last pass as NVLink peer stores (default), or NCCL all-to-all")
     args = ap.parse_args()
@@ -611,7 +611,7 @@ def main():
             except Exception as ex:   # noqa: BLE001
                 line["proof"] = {"error": repr(ex)[:300]}
         if args.all_gates_proof_log_n:
-            # the gate mix of the real circuit: 19 gate kinds evaluated from bytecode (gate_vm.h)
+            # the gate mix of the real circuit: 22 gate kinds evaluated from bytecode (gate_vm.h)
             try:
                 line["proof_all_gates"] = proof_section(E, args.all_gates_proof_log_n, reps=3, all_gates=True)
             except Exception as ex:   # noqa: BLE001

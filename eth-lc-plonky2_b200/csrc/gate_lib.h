@@ -2,7 +2,8 @@
 // in SURVEY.md A.8 and DESIGN.md 6.  Host code.  [DEP plonky2:gates/{constant,public_input,arithmetic_base,poseidon,base_sum,
 // arithmetic_extension,multiplication_extension,reducing,reducing_extension,random_access,exponentiation,poseidon_mds,
 // coset_interpolation}.rs]
-// [DEP plonky2_crypto (plonky2_u32):gates/{arithmetic_u32,add_many_u32,subtraction_u32,range_check_u32,comparison}.rs]
+// [DEP plonky2_crypto (plonky2_u32):gates/{arithmetic_u32,add_many_u32,subtraction_u32,range_check_u32,comparison,
+//      interleave_u32,uninterleave_to_u32,uninterleave_to_b32}.rs]
 // Tier C of SURVEY.md Appendix A: wire layouts and constraint ORDER are recalled, not checked against the absent source;
 // with a Rust toolchain the programs are RECORDED from the gates' own eval_unfiltered_circuit instead and
 // these builders become test fixtures.  Constraint t of a gate receives alpha^t, so order is part of the contract.
@@ -17,7 +18,8 @@ enum PlkGateKind : u32 {
     PLK_NOOP = 0, PLK_CONSTANT = 1, PLK_PUBLIC_INPUT = 2, PLK_ARITHMETIC = 3, PLK_POSEIDON = 4, PLK_BASE_SUM = 5,
     PLK_ARITHMETIC_EXT = 6, PLK_MUL_EXT = 7, PLK_REDUCING = 8, PLK_REDUCING_EXT = 9, PLK_RANDOM_ACCESS = 10,
     PLK_EXPONENTIATION = 11, PLK_POSEIDON_MDS = 12, PLK_U32_ARITHMETIC = 13, PLK_U32_ADD_MANY = 14, PLK_U32_SUBTRACTION = 15,
-    PLK_U32_RANGE_CHECK = 16, PLK_COMPARISON = 17, PLK_COSET_INTERPOLATION = 18, PLK_NUM_KINDS = 19,
+    PLK_U32_RANGE_CHECK = 16, PLK_COMPARISON = 17, PLK_COSET_INTERPOLATION = 18,
+    PLK_U32_INTERLEAVE = 19, PLK_UNINTERLEAVE_TO_U32 = 20, PLK_UNINTERLEAVE_TO_B32 = 21, PLK_NUM_KINDS = 22,
     PLK_CUSTOM = 255   // no library builder: the program came over the ABI (recorded on the Rust side)
 };
 
@@ -32,6 +34,7 @@ static inline u32 plk_gate_degree(u32 kind, const u32 p[4]) {
         case PLK_U32_ARITHMETIC: case PLK_U32_ADD_MANY: case PLK_U32_SUBTRACTION: case PLK_U32_RANGE_CHECK: case PLK_EXPONENTIATION: return 4;
         case PLK_COMPARISON: return 1u << ((p[0] + p[1] - 1) / p[1]);
         case PLK_COSET_INTERPOLATION: return p[1];
+        case PLK_U32_INTERLEAVE: case PLK_UNINTERLEAVE_TO_U32: case PLK_UNINTERLEAVE_TO_B32: return 2;
         case PLK_RANDOM_ACCESS: return p[0] + 1;
         case PLK_POSEIDON: return 7;
     }
@@ -92,6 +95,19 @@ struct RandomAccessLayout {
     GL_HD u32 bit(u32 i, u32 c) const { return num_routed() + c * bits + i; }
 };
 
+struct InterleaveLayout {   // U32InterleaveGate: per op x, x_interleaved (routed), then 32 bits per op
+    u32 num_ops;
+    GL_HD u32 x(u32 i) const { return 2 * i; }
+    GL_HD u32 x_interleaved(u32 i) const { return 2 * i + 1; }
+    GL_HD u32 bit(u32 i, u32 j) const { return 2 * num_ops + 32 * i + j; }
+};
+struct UninterleaveLayout {   // UninterleaveToU32Gate / UninterleaveToB32Gate: per op x_interleaved, evens, odds (routed), then 64 bits per op
+    u32 num_ops;
+    GL_HD u32 x_interleaved(u32 i) const { return 3 * i; }
+    GL_HD u32 evens(u32 i) const { return 3 * i + 1; }
+    GL_HD u32 odds(u32 i) const { return 3 * i + 2; }
+    GL_HD u32 bit(u32 i, u32 j) const { return 3 * num_ops + 64 * i + j; }
+};
 struct CosetInterpLayout {   // CosetInterpolationGate { subgroup_bits, degree }, D = 2 (recursive FRI verifier: interpolate_coset)
     u32 subgroup_bits, degree;
     GL_HD u32 num_points() const { return 1u << subgroup_bits; }
@@ -458,6 +474,43 @@ GL_HD bool plk_build_gate(BT &B, u32 kind, const u32 p[4], u32 num_wires, u32 nu
         for (u32 i = 0; i <= cb; i++) B.emit(B.mul(bits[i], B.sub(one, bits[i])));
         B.emit(B.sub(B.add(B.imm(1ull << cb), B.wire(L.msd())), B.reduce_with_powers(bits, cb + 1, 2)));
         B.emit(B.sub(B.wire(L.result()), bits[cb]));
+        return true;
+    }
+    case PLK_U32_INTERLEAVE: {   // bits boolean; x = sum b_j 2^j; x_interleaved = sum b_j 4^j (a zero bit between every two bits)
+        InterleaveLayout L = {p[0]};
+        if (p[0] == 0 || 2 * p[0] > num_routed || L.bit(p[0] - 1, 31) >= num_wires) return false;
+        for (u32 i = 0; i < L.num_ops; i++) {
+            V lin = B.imm(0), spread = B.imm(0);
+            for (int j = 31; j >= 0; j--) {
+                const V b = B.wire(L.bit(i, (u32)j));
+                B.emit(B.mul(b, B.sub(one, b)));
+                lin = j == 31 ? b : B.mad(lin, B.imm(2), b);
+                spread = j == 31 ? b : B.mad(spread, B.imm(4), b);
+            }
+            B.emit(B.sub(B.wire(L.x(i)), lin));
+            B.emit(B.sub(B.wire(L.x_interleaved(i)), spread));
+        }
+        return true;
+    }
+    case PLK_UNINTERLEAVE_TO_U32: case PLK_UNINTERLEAVE_TO_B32: {
+        // 64 bits of x_interleaved; the even-position and the odd-position bits are packed densely (to U32: base 2) or
+        // stay spread out (to B32: base 4)
+        UninterleaveLayout L = {p[0]};
+        if (p[0] == 0 || 3 * p[0] > num_routed || L.bit(p[0] - 1, 63) >= num_wires) return false;
+        const u64 base = kind == PLK_UNINTERLEAVE_TO_U32 ? 2 : 4;
+        for (u32 i = 0; i < L.num_ops; i++) {
+            V all = B.imm(0), ev = B.imm(0), od = B.imm(0);
+            for (int j = 63; j >= 0; j--) {
+                const V b = B.wire(L.bit(i, (u32)j));
+                B.emit(B.mul(b, B.sub(one, b)));
+                all = j == 63 ? b : B.mad(all, B.imm(2), b);
+                if (j & 1) od = j == 63 ? b : B.mad(od, B.imm(base), b);
+                else ev = j == 62 ? b : B.mad(ev, B.imm(base), b);
+            }
+            B.emit(B.sub(B.wire(L.x_interleaved(i)), all));
+            B.emit(B.sub(B.wire(L.evens(i)), ev));
+            B.emit(B.sub(B.wire(L.odds(i)), od));
+        }
         return true;
     }
     case PLK_COSET_INTERPOLATION:

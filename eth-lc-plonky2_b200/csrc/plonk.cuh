@@ -413,6 +413,7 @@ GL_HD void quot_native_point(const QuotParams &p, u64 t) {
         PLK_NATIVE_CASE(PLK_RANDOM_ACCESS) PLK_NATIVE_CASE(PLK_EXPONENTIATION) PLK_NATIVE_CASE(PLK_POSEIDON_MDS)
         PLK_NATIVE_CASE(PLK_U32_ARITHMETIC) PLK_NATIVE_CASE(PLK_U32_ADD_MANY) PLK_NATIVE_CASE(PLK_U32_SUBTRACTION)
         PLK_NATIVE_CASE(PLK_U32_RANGE_CHECK) PLK_NATIVE_CASE(PLK_COMPARISON)
+        PLK_NATIVE_CASE(PLK_U32_INTERLEAVE) PLK_NATIVE_CASE(PLK_UNINTERLEAVE_TO_U32) PLK_NATIVE_CASE(PLK_UNINTERLEAVE_TO_B32)
 #undef PLK_NATIVE_CASE
 #pragma unroll
         for (int c = 0; c < PLK_MAX_CHALLENGES; c++) total[c] = gl_mul_add(filter, acc.sum[c], total[c]);
@@ -425,7 +426,8 @@ GL_HD void quot_native_point(const QuotParams &p, u64 t) {
 // the compiled evaluators are spread over three kernels by code size (arithmetic + recursion / lookups + exponentiation / u32)
 #define PLK_NATIVE_GROUP_A ((1u << PLK_CONSTANT) | (1u << PLK_PUBLIC_INPUT) | (1u << PLK_ARITHMETIC) | (1u << PLK_BASE_SUM) | (1u << PLK_ARITHMETIC_EXT) | (1u << PLK_MUL_EXT) | (1u << PLK_REDUCING) | (1u << PLK_REDUCING_EXT))
 #define PLK_NATIVE_GROUP_B ((1u << PLK_RANDOM_ACCESS) | (1u << PLK_EXPONENTIATION) | (1u << PLK_POSEIDON_MDS))
-#define PLK_NATIVE_GROUP_C ((1u << PLK_U32_ARITHMETIC) | (1u << PLK_U32_ADD_MANY) | (1u << PLK_U32_SUBTRACTION) | (1u << PLK_U32_RANGE_CHECK) | (1u << PLK_COMPARISON))
+#define PLK_NATIVE_GROUP_C ((1u << PLK_U32_ARITHMETIC) | (1u << PLK_U32_ADD_MANY) | (1u << PLK_U32_SUBTRACTION) | (1u << PLK_U32_RANGE_CHECK) | (1u << PLK_COMPARISON) | \
+                            (1u << PLK_U32_INTERLEAVE) | (1u << PLK_UNINTERLEAVE_TO_U32) | (1u << PLK_UNINTERLEAVE_TO_B32))
 #define PLK_NATIVE_KINDS (PLK_NATIVE_GROUP_A | PLK_NATIVE_GROUP_B | PLK_NATIVE_GROUP_C)
 
 // * 1 / Z_H(x); position -> natural index

@@ -392,7 +392,7 @@ PolynomialBatch.prove_openings = staticmethod(_prove_openings)
 # ---------------------------------------------------------------- a5 / a6 / prove / verify
 GATE_KINDS = ("Noop", "Constant", "PublicInput", "Arithmetic", "Poseidon", "BaseSum", "ArithmeticExtension", "MulExtension", "Reducing",
               "ReducingExtension", "RandomAccess", "Exponentiation", "PoseidonMds", "U32Arithmetic", "U32AddMany", "U32Subtraction",
-              "U32RangeCheck", "Comparison", "CosetInterpolation")
+              "U32RangeCheck", "Comparison", "CosetInterpolation", "U32Interleave", "UninterleaveToU32", "UninterleaveToB32")
 BLOB_V2_MAGIC = 0x32424B4C50
 ALL_GATES = (1 << len(GATE_KINDS)) - 1
 
@@ -415,7 +415,7 @@ def synth_circuit(degree_bits, seed=1):
 
 
 def synth_circuit_v2(degree_bits, seed=1, kinds_mask=ALL_GATES):
-    """Synthetic circuit over the gates of `kinds_mask` (bit k = GATE_KINDS[k]; default: all 19) with a satisfying witness,
+    """Synthetic circuit over the gates of `kinds_mask` (bit k = GATE_KINDS[k]; default: all 22) with a satisfying witness,
     selector groups formed by plonky2's rule, version-2 description with the gates' bytecode (eng_synth_circuit_v2; host code)."""
     n = 1 << degree_bits
     consts = np.zeros((8, n), np.uint64)

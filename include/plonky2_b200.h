@@ -218,8 +218,8 @@ eng_status eng_blob_free(uint64_t *blob);
  *   2 PublicInput, 3 Arithmetic{p0 ops}, 4 Poseidon, 5 BaseSum<p0>{p1 limbs}, 6 ArithmeticExtension{p0}, 7 MulExtension{p0},
  *   8 Reducing{p0 coeffs}, 9 ReducingExtension{p0}, 10 RandomAccess{p0 bits, p1 copies, p2 extra constants},
  *   11 Exponentiation{p0 bits}, 12 PoseidonMds, 13 U32Arithmetic{p0}, 14 U32AddMany{p0 addends, p1 ops}, 15 U32Subtraction{p0},
- *   16 U32RangeCheck{p0 limbs}, 17 Comparison{p0 bits, p1 chunks}, 18 CosetInterpolation{p0 subgroup bits, p1 degree};
- *   255 = custom (the program is mandatory).  A library gate whose program is the library's own runs through the evaluators
+ *   16 U32RangeCheck{p0 limbs}, 17 Comparison{p0 bits, p1 chunks}, 18 CosetInterpolation{p0 subgroup bits, p1 degree},
+ *   19 U32Interleave{p0 ops}, 20 UninterleaveToU32{p0 ops}, 21 UninterleaveToB32{p0 ops}; 255 = custom (the program is mandatory).  A library gate whose program is the library's own runs through the evaluators
  *   compiled from the same source (option quot_native_gates); anything else through the bytecode interpreter.
  * Version 1 (the five core gates, kept for round-1 callers): the 12 header words, (kind, selector_index, group.start,
  *   group.end) x num_gates, circuit_digest x 4.

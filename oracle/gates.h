@@ -7,7 +7,7 @@
  *   [DEP plonky2:gates/{base_sum,arithmetic_extension,multiplication_extension,reducing,reducing_extension,random_access,
  *        exponentiation,poseidon_mds,coset_interpolation}.rs]
  *   [DEP plonky2_crypto @3f71378 (plonky2_u32 gates):gates/{arithmetic_u32,add_many_u32,subtraction_u32,range_check_u32,
- *        comparison}.rs]
+ *        comparison,interleave_u32,uninterleave_to_u32,uninterleave_to_b32}.rs]
  * Written as formulas over a generic field (O = OpsBase for the prover's points, OpsExt for the verifier's zeta); the engine
  * evaluates the same gates from BYTECODE (eth-lc-plonky2_b200/csrc/gate_lib.h), so agreement of the two is a cross-check of
  * two independently written forms.  Wire layouts are spelled out per gate below (not shared with the product).
@@ -22,7 +22,7 @@ enum {
     ORC_G_BASE_SUM = 5, ORC_G_ARITHMETIC_EXT = 6, ORC_G_MUL_EXT = 7, ORC_G_REDUCING = 8, ORC_G_REDUCING_EXT = 9,
     ORC_G_RANDOM_ACCESS = 10, ORC_G_EXPONENTIATION = 11, ORC_G_POSEIDON_MDS = 12, ORC_G_U32_ARITHMETIC = 13,
     ORC_G_U32_ADD_MANY = 14, ORC_G_U32_SUBTRACTION = 15, ORC_G_U32_RANGE_CHECK = 16, ORC_G_COMPARISON = 17,
-    ORC_G_COSET_INTERPOLATION = 18
+    ORC_G_COSET_INTERPOLATION = 18, ORC_G_U32_INTERLEAVE = 19, ORC_G_UNINTERLEAVE_TO_U32 = 20, ORC_G_UNINTERLEAVE_TO_B32 = 21
 };
 
 /* an element of the extension algebra spread over two wires */
@@ -247,6 +247,30 @@ bool orc_eval_gate_ext(int kind, const int p[4], const typename O::T *w, const t
         }
         const OrcPair<O> out = orc_pair_at<O>(w, w_value);
         emit(O::sub(out.x, ev.x)); emit(O::sub(out.y, ev.y));
+        return true;
+    }
+    case ORC_G_U32_INTERLEAVE: {   /* op i: x at 2 i, x_interleaved at 2 i + 1; 32 bits at 2 ops + 32 i (little-endian) */
+        const int ops = p[0];
+        for (int i = 0; i < ops; i++) {
+            const T *bits = w + 2 * ops + 32 * i;
+            for (int j = 31; j >= 0; j--) emit(O::mul(bits[j], O::sub(one, bits[j])));
+            emit(O::sub(w[2 * i], orc_horner<O>(bits, 1, 32, 2)));
+            emit(O::sub(w[2 * i + 1], orc_horner<O>(bits, 1, 32, 4)));
+        }
+        return true;
+    }
+    case ORC_G_UNINTERLEAVE_TO_U32: case ORC_G_UNINTERLEAVE_TO_B32: {
+        /* op i: x_interleaved, evens, odds at 3 i ..; 64 bits at 3 ops + 64 i; evens / odds collect every second bit, packed
+         * with base 2 (to U32) or left spread with base 4 (to B32) */
+        const int ops = p[0];
+        const u64 base = kind == ORC_G_UNINTERLEAVE_TO_U32 ? 2 : 4;
+        for (int i = 0; i < ops; i++) {
+            const T *bits = w + 3 * ops + 64 * i;
+            for (int j = 63; j >= 0; j--) emit(O::mul(bits[j], O::sub(one, bits[j])));
+            emit(O::sub(w[3 * i], orc_horner<O>(bits, 1, 64, 2)));
+            emit(O::sub(w[3 * i + 1], orc_horner<O>(bits, 2, 32, base)));
+            emit(O::sub(w[3 * i + 2], orc_horner<O>(bits + 1, 2, 32, base)));
+        }
         return true;
     }
     }

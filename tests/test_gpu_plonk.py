@@ -69,12 +69,12 @@ def test_invalid_witness_gives_a_proof_that_does_not_verify(engine, oracle):
 # ---- gates as bytecode (row a6 for the real gate set), product verifier (f4), circuit cache (f2) ----
 @pytest.mark.parametrize("db", [5, 8, 11])
 def test_all_gate_kinds_prove_matches_oracle_and_verifies(engine, oracle, db):
-    """19 gate kinds (core, recursion, plonky2_crypto u32) in one circuit: the engine interprets the gates' bytecode, the
+    """22 gate kinds (core, recursion, plonky2_crypto u32) in one circuit: the engine interprets the gates' bytecode, the
     oracle evaluates its own formulas (oracle/gates.h); proofs identical word for word, both verifiers accept."""
     E = engine
     s = E.synth_circuit_v2(db, seed=200 + db)
     circ = E.Circuit.build(s)
-    assert circ.info.num_gates == len(E.GATE_KINDS) == 19
+    assert circ.info.num_gates == len(E.GATE_KINDS) == 22
     proof, ms = circ.prove(s["wires"], s["pi_hash"])
     oc = oracle.Circuit(s["blob"])
     ocs = oracle.Batch.from_values(np.concatenate([s["constants"], s["sigmas"]]), 3, 4)

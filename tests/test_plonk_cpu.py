@@ -125,7 +125,7 @@ def test_all_gate_kinds_oracle_prove_then_verify(oracle, synth_v2, db):
 @pytest.mark.parametrize("native", [3, 2, 1, 0], ids=["compiled+poseidon_fp64", "compiled+poseidon_bytecode", "bytecode+poseidon_fp64", "all_bytecode"])
 def test_all_gate_kinds_quotient_replay(emu, oracle, synth_v2, native):
     """Bytecode (gate_lib.h through the interpreter), the COMPILED evaluators (the same gate_lib.h source instantiated with the
-    in-place builder model) and formulas (oracle/gates.h) for all 19 gate kinds, through the quotient kernels' bodies."""
+    in-place builder model) and formulas (oracle/gates.h) for all 22 gate kinds, through the quotient kernels' bodies."""
     _quotient_replay(emu, oracle, synth_v2[5], 5, native)
 
 
