@@ -612,7 +612,7 @@ eng_status eng_shutdown(void) {
     cudaDeviceSynchronize();
     for (void *p : g.table_allocs) cudaFree(p);
     g.table_allocs.clear();
-    g.tables.tw_local_cache.clear(); g.tables.w2_cache.clear(); g.tables.shift_cache.clear(); g.pow_cache.clear();
+    g.tables.tw_local_cache.clear(); g.tables.tau_cache.clear(); g.tables.w2_cache.clear(); g.tables.shift_cache.clear(); g.pow_cache.clear();
     for (auto &ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
     if (g.own_stream) cudaStreamDestroy(g.own_stream);
     if (g.copy_stream) cudaStreamDestroy(g.copy_stream);

@@ -56,6 +56,12 @@ struct NttPass {
     // moment the G ranks of the box store into G DIFFERENT destinations instead of all hammering shard 0, then 1, ...
     u64 tile_rot;
     const u64 *tw_local;  // w_P^e (or inverse), e < P
+    // tau tables of the non-final radix-16 rounds, round after round: [r - 1][lo] = w_P^(bitrev4(r) * (lo << t0)), r = 1..15,
+    // lo < 2^(log_p - t0 - 4).  Consecutive threads hold consecutive lo, so the 15 tau loads of a block are conflict-free;
+    // indexing the w_P^e table with bitrev4(r) * (lo << t0) instead strides by up to 256 bytes between threads (ncu, round 2:
+    // 429 M of the 495 M shared-memory wavefronts of those loads were bank-conflict replays).
+    const u64 *tau_tab;
+    u32 tau_in_smem;      // the kernel stages tau_tab in shared memory (it fits); otherwise it is read through L1
     const u64 *w_lo, *w_hi;  // w_n^e = w_hi[e >> w_lo_bits] * w_lo[e & mask]   (or inverse powers)
     u32 w_lo_bits;
     const u64 *shift_a, *shift_b;  // LDE: s_e^{j*st} [e][P]  and  s_e^{r} [e][st];  s_e = 7 * w_L^e
@@ -72,10 +78,29 @@ GL_HD u32 ntt_brev(u32 x, u32 bits) {
 #endif
 }
 
-GL_HD u32 ntt_pitch(u32 log_p) { u32 P = 1u << log_p; return P + (P >> 4) + 1; }
+// Lane pitch.  P + P/16 keeps both access patterns of the rounds conflict-free; the pad decides the strided LOAD phase,
+// where the lane index runs fastest over the threads: with A lanes a warp stores (a, j), a < A, j < 32 / A, and
+// a * pitch + j must hit 32 different 8-byte slots mod 32: pitch = 32 / A (mod 32) (1 for P < 32).
+GL_HD u32 ntt_pitch(u32 log_p, u32 log_a) {
+    const u32 P = 1u << log_p, base = P + (P >> 4);
+    if (log_p < 5 || log_a == 0 || log_a > 5) return base + 1;
+    const u32 want = 32u >> log_a;                       // 32 / A
+    return base + ((want + 32u - (base & 31u)) & 31u);
+}
 GL_HD u32 ntt_sm(u32 pitch, u32 a, u32 j) { return a * pitch + j + (j >> 4); }
-static inline size_t ntt_smem_bytes(u32 log_p, u32 log_a) {  // tile + the w_P^e table (all P powers)
-    return ((size_t)ntt_pitch(log_p) * (1u << log_a) + (1u << log_p) + 1) * sizeof(u64);
+// entries of the tau tables of a P-point network (the rounds: a remainder round of log_p mod 4 stages, then radix-16)
+GL_HD u32 ntt_tau_entries(u32 log_p) {
+    u32 total = 0;
+    for (u32 t0 = log_p & 3; t0 + 4 < log_p; t0 += 4) total += 15u << (log_p - t0 - 4);
+    return total;
+}
+#define NTT_SMEM_LIMIT (227u * 1024u)
+static inline size_t ntt_smem_bytes_base(u32 log_p, u32 log_a) {  // tile + the w_P^e table (all P powers)
+    return ((size_t)ntt_pitch(log_p, log_a) * (1u << log_a) + (1u << log_p) + 1) * sizeof(u64);
+}
+static inline bool ntt_tau_fits(u32 log_p, u32 log_a) { return ntt_smem_bytes_base(log_p, log_a) + (size_t)ntt_tau_entries(log_p) * 8 <= NTT_SMEM_LIMIT; }
+static inline size_t ntt_smem_bytes(u32 log_p, u32 log_a) {
+    return ntt_smem_bytes_base(log_p, log_a) + (ntt_tau_fits(log_p, log_a) ? (size_t)ntt_tau_entries(log_p) * 8 : 0);
 }
 
 GL_HD u64 ntt_twiddle2(const NttPass &p, u64 e) {
@@ -91,7 +116,7 @@ GL_HD u64 ntt_twiddle2(const NttPass &p, u64 e) {
 #endif
 template <int MODE>
 GL_HD void ntt_load(const NttPass &p, u64 *sm, u64 tile, u32 tid, u32 nthreads) {
-    const u32 P = 1u << p.log_p, A = 1u << p.log_a, pitch = ntt_pitch(p.log_p);
+    const u32 P = 1u << p.log_p, A = 1u << p.log_a, pitch = ntt_pitch(p.log_p, p.log_a);
     const u32 total = P << p.log_a;
     constexpr int B = NTT_LOAD_BATCH;
     if (MODE == NTT_LDE_FIRST || MODE == NTT_INTT_P1 || MODE == NTT_INTT_P2) {
@@ -198,7 +223,7 @@ GL_HD void ntt_load(const NttPass &p, u64 *sm, u64 tile, u32 tid, u32 nthreads) 
 // there the twiddle of a butterfly depends only on its register index, and the ones that are 1 are skipped.
 template <int R, bool LAST>
 GL_HD void ntt_round(const NttPass &p, u64 *sm, const u64 *tw, u32 t0, u32 tid, u32 nthreads) {
-    const u32 P = 1u << p.log_p, pitch = ntt_pitch(p.log_p);
+    const u32 P = 1u << p.log_p, pitch = ntt_pitch(p.log_p, p.log_a);
     const u32 blocks_per_lane = P >> R;
     const u32 nblocks = blocks_per_lane << p.log_a;
     const u32 log_js = p.log_p - t0 - R;  // log2 of the element stride inside the register block
@@ -421,9 +446,10 @@ GL_HD void ntt16_stage(gl96 (&x)[16]) {
 }
 
 // One radix-16 round (stages t0+1 .. t0+4).  `tw` holds w_P^e for ALL e < P (inverse powers when INV).
+// tau: this round's table (unused when LAST)
 template <bool LAST, bool INV>
-GL_HD void ntt_round16(const NttPass &p, u64 *sm, const u64 *tw, u32 t0, u32 tid, u32 nthreads) {
-    const u32 P = 1u << p.log_p, pitch = ntt_pitch(p.log_p);
+GL_HD void ntt_round16(const NttPass &p, u64 *sm, const u64 *tau, u32 t0, u32 tid, u32 nthreads) {
+    const u32 P = 1u << p.log_p, pitch = ntt_pitch(p.log_p, p.log_a);
     const u32 blocks_per_lane = P >> 4, log_bpl = p.log_p - 4;
     const u32 nblocks = blocks_per_lane << p.log_a;
     const u32 log_js = p.log_p - t0 - 4;
@@ -441,11 +467,11 @@ GL_HD void ntt_round16(const NttPass &p, u64 *sm, const u64 *tw, u32 t0, u32 tid
         ntt16_stage<2, INV>(x);
         ntt16_stage<3, INV>(x);
         ntt16_stage<4, INV>(x);
-        const u32 E = lo << t0;   // tau = w_P^E; register r carries tau^bitrev4(r)
+        // register r carries tau^bitrev4(r), tau = w_P^(lo << t0): row r - 1 of the round's table at column lo
 #pragma unroll
         for (int r = 0; r < 16; r++) {
             u64 o = l3_reduce(x[r]);
-            if (!LAST && r != 0) o = gl_mul(o, tw[(u32)ntt_brev4(r) * E]);
+            if (!LAST && r != 0) o = gl_mul(o, tau[((u32)(r - 1) << log_js) + lo]);
             sm[linear ? base + (u32)r * step : ntt_sm(pitch, a, jb + ((u32)r << log_js))] = o;
         }
     }
@@ -454,7 +480,7 @@ GL_HD void ntt_round16(const NttPass &p, u64 *sm, const u64 *tw, u32 t0, u32 tid
 // ---- phase 3: shared -> global; slot q of a lane holds frequency brev(q) ----
 template <int MODE>
 GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nthreads) {
-    const u32 P = 1u << p.log_p, A = 1u << p.log_a, pitch = ntt_pitch(p.log_p);
+    const u32 P = 1u << p.log_p, A = 1u << p.log_a, pitch = ntt_pitch(p.log_p, p.log_a);
     const u32 total = P << p.log_a;
     const u32 log_st = p.log_n - p.log_p;
     if (MODE == NTT_LDE_FIRST) {
@@ -572,8 +598,9 @@ GL_HD void ntt_store(const NttPass &p, const u64 *sm, u64 tile, u32 tid, u32 nth
         if (rem == 1) { if (p.log_p == 1) ntt_round<1, true>(p, sm, tw, t0, tid, nthreads); else ntt_round<1, false>(p, sm, tw, t0, tid, nthreads); t0 += 1; SYNC; } \
         if (rem == 2) { if (p.log_p == 2) ntt_round<2, true>(p, sm, tw, t0, tid, nthreads); else ntt_round<2, false>(p, sm, tw, t0, tid, nthreads); t0 += 2; SYNC; } \
         if (rem == 3) { if (p.log_p == 3) ntt_round<3, true>(p, sm, tw, t0, tid, nthreads); else ntt_round<3, false>(p, sm, tw, t0, tid, nthreads); t0 += 3; SYNC; } \
-        for (; t0 + 4 < p.log_p; t0 += 4) { ntt_round16<false, INV>(p, sm, tw, t0, tid, nthreads); SYNC; }      \
-        if (t0 < p.log_p) { ntt_round16<true, INV>(p, sm, tw, t0, tid, nthreads); SYNC; }                       \
+        const u64 *tau_r = tau;                                                                                 \
+        for (; t0 + 4 < p.log_p; t0 += 4) { ntt_round16<false, INV>(p, sm, tau_r, t0, tid, nthreads); tau_r += 15u << (p.log_p - t0 - 4); SYNC; } \
+        if (t0 < p.log_p) { ntt_round16<true, INV>(p, sm, tau_r, t0, tid, nthreads); SYNC; }                    \
     }
 
 #ifdef __CUDACC__
@@ -587,10 +614,14 @@ template <int MODE>
 __global__ void __launch_bounds__(NTT_LB_THREADS, NTT_MINB) ntt_pass_kernel(NttPass p) {
     extern __shared__ u64 ntt_smem[];
     u64 *sm = ntt_smem;
-    u64 *tw_s = ntt_smem + (size_t)ntt_pitch(p.log_p) * (1u << p.log_a);   // w_P^e table staged once per CTA
+    u64 *tw_s = ntt_smem + (size_t)ntt_pitch(p.log_p, p.log_a) * (1u << p.log_a);   // w_P^e table staged once per CTA
+    u64 *tau_s = tw_s + (1u << p.log_p) + 1;                                          // ... and the tau tables, if they fit
     const u32 tid = threadIdx.x, nthreads = blockDim.x;
     for (u32 i = tid; i < (1u << p.log_p); i += nthreads) tw_s[i] = p.tw_local[i];
+    if (p.tau_in_smem)
+        for (u32 i = tid, n_tau = ntt_tau_entries(p.log_p); i < n_tau; i += nthreads) tau_s[i] = p.tau_tab[i];
     const u64 *tw = tw_s;
+    const u64 *tau = p.tau_in_smem ? tau_s : p.tau_tab;
     for (u64 tile_i = blockIdx.x; tile_i < p.num_tiles; tile_i += gridDim.x) {
         u64 tile = tile_i + p.tile_rot;
         if (tile >= p.num_tiles) tile -= p.num_tiles;

@@ -39,6 +39,28 @@ struct NttTableStore {
         if (!d) return nullptr;            // a failed upload is not cached (the owner reports it)
         return tw_local_cache[key] = d;
     }
+    // tau tables of the non-final radix-16 rounds of a P-point network (layout: NttPass::tau_tab)
+    std::map<std::pair<int, int>, const u64 *> tau_cache;
+    const u64 *tau_tab(int log_p, bool inverse) {
+        auto key = std::make_pair(log_p, (int)inverse);
+        auto it = tau_cache.find(key);
+        if (it != tau_cache.end()) return it->second;
+        u64 w = h_gl_root_of_unity(log_p);
+        if (inverse) w = h_gl_inv(w);
+        std::vector<u64> t;
+        for (u32 t0 = (u32)log_p & 3; t0 + 4 < (u32)log_p; t0 += 4) {
+            const u32 log_js = (u32)log_p - t0 - 4;
+            for (u32 r = 1; r < 16; r++) {
+                const u64 step = h_gl_pow(w, (u64)ntt_brev4((int)r) << t0);       // w_P^(bitrev4(r) << t0)
+                u64 v = 1;
+                for (u32 lo = 0; lo < (1u << log_js); lo++) { t.push_back(v); v = h_gl_mul(v, step); }
+            }
+        }
+        if (t.empty()) t.push_back(1);         // networks without a non-final radix-16 round: a valid (unused) pointer
+        const u64 *d = upload(t);
+        if (!d) return nullptr;
+        return tau_cache[key] = d;
+    }
     // two-level powers of w_n (inverse: w_n^-1)
     W2 w2(int log_n, bool inverse) {
         auto key = std::make_pair(log_n, (int)inverse);
@@ -108,6 +130,7 @@ static inline u32 ntt_log_a_contig(u32 log_p) {
 static inline NttLaunch ntt_make_launch(int mode, const NttPass &p) {
     NttLaunch l;
     l.mode = mode; l.p = p;
+    l.p.tau_in_smem = ntt_tau_fits(p.log_p, p.log_a) ? 1 : 0;
     l.threads = ntt_threads(p.log_p, p.log_a);
     l.smem = ntt_smem_bytes(p.log_p, p.log_a);
     return l;
@@ -127,6 +150,8 @@ static inline bool ntt_plan_intt(NttTableStore &ts, const u64 *in, u64 in_stride
         p.log_p = log_n; p.log_a = ntt_log_a_contig(log_n);
         p.num_tiles = ((u64)C + (1u << p.log_a) - 1) >> p.log_a;
         p.tw_local = ts.tw_local(log_n, true);
+
+        p.tau_tab = ts.tau_tab(log_n, true); p.tau_in_smem = 0;
         plan.push_back(ntt_make_launch(NTT_INTT_SINGLE, p));
         return true;
     }
@@ -138,12 +163,16 @@ static inline bool ntt_plan_intt(NttTableStore &ts, const u64 *in, u64 in_stride
     p.log_p = l2; p.log_a = ntt_log_a_strided(l2, l1);
     p.num_tiles = (u64)C << (l1 - p.log_a);
     p.tw_local = ts.tw_local(l2, true);
+
+    p.tau_tab = ts.tau_tab(l2, true); p.tau_in_smem = 0;
     plan.push_back(ntt_make_launch(NTT_INTT_P1, p));
     // pass 2: tiles over k2
     p.in = scratch; p.in_col_stride = scratch_stride; p.out = out; p.out_col_stride = out_stride;
     p.log_p = l1; p.log_a = ntt_log_a_strided(l1, l2);
     p.num_tiles = (u64)C << (l2 - p.log_a);
     p.tw_local = ts.tw_local(l1, true);
+
+    p.tau_tab = ts.tau_tab(l1, true); p.tau_in_smem = 0;
     plan.push_back(ntt_make_launch(NTT_INTT_P2, p));
     return true;
 }
@@ -179,6 +208,8 @@ static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs
         u64 units = (u64)C << rate_bits;
         p.num_tiles = (units + (1u << p.log_a) - 1) >> p.log_a;
         p.tw_local = ts.tw_local(log_n, false);
+
+        p.tau_tab = ts.tau_tab(log_n, false); p.tau_in_smem = 0;
         set_shard_ptrs(p);
         plan.push_back(ntt_make_launch(NTT_LDE_SINGLE, p));
         return true;
@@ -191,6 +222,8 @@ static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs
     p.log_p = lp; p.log_a = ntt_log_a_strided(lp, lst);
     p.num_tiles = ((u64)C << rate_bits) << (lst - p.log_a);
     p.tw_local = ts.tw_local(lp, false);
+
+    p.tau_tab = ts.tau_tab(lp, false); p.tau_in_smem = 0;
     plan.push_back(ntt_make_launch(NTT_LDE_FIRST, p));
     // last pass: contiguous runs of 2^lst points, in place over the whole LDE buffer
     p.in = lde;
@@ -199,6 +232,8 @@ static inline bool ntt_plan_lde(NttTableStore &ts, const u64 *coeffs, u64 coeffs
     p.num_units = units;
     p.num_tiles = (units + (1u << p.log_a) - 1) >> p.log_a;
     p.tw_local = ts.tw_local(lst, false);
+
+    p.tau_tab = ts.tau_tab(lst, false); p.tau_in_smem = 0;
     set_shard_ptrs(p);
     if (shard_out && (p.num_tiles % ((u64)1 << log_shards)) == 0)
         p.tile_rot = (p.num_tiles >> log_shards) * (first_shard & ((1u << log_shards) - 1));

@@ -39,8 +39,8 @@ static void replay_round(const NttPass &p, u64 *sm, u32 t0, u32 threads) {
     for (u32 t = 0; t < threads; t++) ntt_round<R, LAST>(p, sm, p.tw_local, t0, t, threads);
 }
 template <bool LAST, bool INV>
-static void replay_round16(const NttPass &p, u64 *sm, u32 t0, u32 threads) {
-    for (u32 t = 0; t < threads; t++) ntt_round16<LAST, INV>(p, sm, p.tw_local, t0, t, threads);
+static void replay_round16(const NttPass &p, u64 *sm, const u64 *tau, u32 t0, u32 threads) {
+    for (u32 t = 0; t < threads; t++) ntt_round16<LAST, INV>(p, sm, tau, t0, t, threads);
 }
 template <bool INV>
 static void replay_rounds(const NttPass &p, u64 *sm, u32 threads) {
@@ -49,8 +49,9 @@ static void replay_rounds(const NttPass &p, u64 *sm, u32 threads) {
     if (rem == 1) { if (p.log_p == 1) replay_round<1, true>(p, sm, t0, threads); else replay_round<1, false>(p, sm, t0, threads); t0 += 1; }
     if (rem == 2) { if (p.log_p == 2) replay_round<2, true>(p, sm, t0, threads); else replay_round<2, false>(p, sm, t0, threads); t0 += 2; }
     if (rem == 3) { if (p.log_p == 3) replay_round<3, true>(p, sm, t0, threads); else replay_round<3, false>(p, sm, t0, threads); t0 += 3; }
-    for (; t0 + 4 < p.log_p; t0 += 4) replay_round16<false, INV>(p, sm, t0, threads);
-    if (t0 < p.log_p) replay_round16<true, INV>(p, sm, t0, threads);
+    const u64 *tau = p.tau_tab;          // same walk through the per-round tables as NTT_ROUNDS
+    for (; t0 + 4 < p.log_p; t0 += 4) { replay_round16<false, INV>(p, sm, tau, t0, threads); tau += 15u << (p.log_p - t0 - 4); }
+    if (t0 < p.log_p) replay_round16<true, INV>(p, sm, tau, t0, threads);
 }
 
 template <int MODE>
