@@ -188,6 +188,10 @@ def proof_section(E, log_n, reps=4, all_gates=False):
     evaluated from bytecode) -- the gate mix of the real circuit.  Wall clock around the call with host wire columns (H2D
     inside).  Every proof is verified (product verifier + the oracle's restatement of plonky2's)."""
     import hashlib
+    try:      # start from an empty pool: a long-lived process that has run other shapes has a fragmented one
+        E.release_cached()
+    except Exception:   # noqa: BLE001
+        pass
     s = E.synth_circuit_v2(log_n, seed=1) if all_gates else E.synth_circuit(log_n, seed=1)
     pinned = True
     try:      # the witness lives in page-locked host memory (eng_host_register), as the e2e contract assumes
@@ -221,8 +225,9 @@ def proof_section(E, log_n, reps=4, all_gates=False):
             "higher_is_better": False, "log_rows": log_n,
             "config": "circuit-shaped synthetic proof, 2^%d rows x 135 wires, %s, standard_recursion_config" % (
                 log_n, "22 gate kinds (core + recursion + u32; bytecode description, library gates compiled)" if all_gates else "5 core gates"),
-            "build_constants_sigmas_commit_s": build_s, "first_call_s": build_s + walls[0],
-            "first_call_note": "Circuit.build (constants||sigmas commit + memory-pool growth for one proof) + the first eng_prove of the process",
+            "build_constants_sigmas_commit_s": build_s, "first_call_in_this_process_s": build_s + walls[0],
+            "first_call_note": "Circuit.build (constants||sigmas commit + memory-pool growth for one proof) + the first eng_prove of this "
+                               "circuit inside the bench process; the cold start of a FRESH process is the line's cold_start object",
             "stage_ms": stages, "proof_u64_words": int(proof.size), "proof_sha256": hashlib.sha256(proof.tobytes()).hexdigest(),
             "verified": verified,
             "reference_published": "~300 s for the real 2^22-row circuit on 32 vCPU (README.md:71); not comparable 1:1"}
@@ -347,6 +352,22 @@ def peer_parity_check(E, plan_cols, rank, world, local_rank, use_peer):
         ex.close()
     dist.barrier()
     return res
+
+
+def cold_start_section(log_n):
+    """Cold start of a prover process (VERDICT r1 task 6): tools/prof_coldstart.py in a FRESH process -- import, eng_init,
+    Circuit.build (constants||sigmas commit + pool growth) and three proofs of the 2^log_n-row synthetic circuit."""
+    import ast
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prof_coldstart.py"), str(log_n), "v1"],
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600)
+    line = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    if res.returncode != 0 or not line:
+        return {"error": "prof_coldstart.py exited %d" % res.returncode}
+    d = ast.literal_eval(line[-1])
+    return {"log_rows": log_n, "eng_init_s": d["eng_init_s"], "circuit_build_s": d["build_s"], "first_proof_s": d["prove_s"][0],
+            "second_proof_s": d["prove_s"][1], "first_call_s": d["build_s"] + d["prove_s"][0], "verified": d["verified"],
+            "note": "fresh process; the memory pool is grown once in Circuit.build (eng_reserve), so the first proof costs what every proof costs; "
+                    "the growth rate (20-60 GB/s) is the driver's and varies from box to box"}
 
 
 def dist_roofline(stages, cols, n, world):
@@ -622,6 +643,13 @@ def main():
                 line["proof_full_size"] = proof_section(E, args.proof_full_log_n, reps=3)
             except Exception as ex:   # noqa: BLE001
                 line["proof_full_size"] = {"error": repr(ex)[:300]}
+        if args.proof_full_log_n and world == 1:
+            try:
+                E.release_cached()
+                torch.cuda.empty_cache()
+                line["cold_start"] = cold_start_section(args.proof_full_log_n)
+            except Exception as ex:   # noqa: BLE001
+                line["cold_start"] = {"error": repr(ex)[:300]}
         if not args.no_cpu_baseline and world == 1:
             try:
                 E.release_cached()    # give the device memory of the proof sections back before the host-side baseline
