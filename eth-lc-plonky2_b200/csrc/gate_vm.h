@@ -168,6 +168,10 @@ struct GvmBuilder {
     }
     // prod_{k < count} (x - k)
     GvmVal range_product(GvmVal x, u32 count) {
+        if (count == 4) {   // x (x - 1)(x - 2)(x - 3) = y (y + 2), y = x (x - 3): two products instead of three (the u32 gates' limbs)
+            GvmVal y = mul(x, sub(x, imm(3)));
+            return mul(y, add(y, imm(2)));
+        }
         GvmVal acc = x;   // (x - 0)
         for (u32 k = 1; k < count; k++) acc = mul(acc, sub(x, imm(k)));
         return acc;

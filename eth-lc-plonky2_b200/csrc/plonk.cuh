@@ -387,6 +387,10 @@ struct QuotDirect {
         return acc2;
     }
     GL_HD V range_product(V x, u32 count) const {
+        if (count == 4) {   // same identity as GvmBuilder::range_product
+            const V y = gl_mul(x, gl_sub(x, 3));
+            return gl_mul(y, gl_add(y, 2));
+        }
         V acc2 = x;
         for (u32 j = 1; j < count; j++) acc2 = gl_mul(acc2, gl_sub(x, (u64)j));
         return acc2;
