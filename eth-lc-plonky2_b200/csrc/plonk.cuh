@@ -107,21 +107,17 @@ GL_HD void plk_poseidon_gate_f64_partial(const W &w, PlkAcc &acc, u64 (&st)[12])
         double nl[12], nh[12];
         pf_circ12(al, PF_T(sc2), PF_T(pair_k_s)[p][0], nl);
         pf_circ12(ah, PF_T(sc2), PF_T(pair_k_s)[p][1], nh);
-#pragma unroll
-        for (int r = 0; r < 12; r++) {
-            nl[r] = pf_fma(al[0], PF_T(col8)[r], nl[r]);
-            nh[r] = pf_fma(ah[0], PF_T(col8)[r], nh[r]);
-        }
-        nl[0] = pf_fma(t0l, 8.0, nl[0]);
-        nh[0] = pf_fma(t0h, 8.0, nh[0]);
         double bl, bh;
         pf_pow7(in1, bl, bh);
-        const double dl = bl - t0l, dh = bh - t0h;   // lane 0 is REPLACED by in1^7: the difference is against the computed b
+        // lane 0 is REPLACED by in1^7: d = in1^7 - (computed b);  both rank-1 terms in one (pf_partial_rounds)
+        const double ul = pf_fma(al[0], 8.0, bl - t0l), uh = pf_fma(ah[0], 8.0, bh - t0h);
 #pragma unroll
         for (int r = 0; r < 12; r++) {
-            al[r] = pf_fma(PF_T(m_col0)[r], dl, nl[r]);
-            ah[r] = pf_fma(PF_T(m_col0)[r], dh, nh[r]);
+            al[r] = pf_fma(PF_T(c_col0)[r], ul, nl[r]);
+            ah[r] = pf_fma(PF_T(c_col0)[r], uh, nh[r]);
         }
+        al[0] = pf_fma(bl, 8.0, al[0]);
+        ah[0] = pf_fma(bh, 8.0, ah[0]);
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) st[i] = pf_fold(al[i], ah[i]);          // state + RC_26

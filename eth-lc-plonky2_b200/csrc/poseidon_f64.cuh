@@ -44,6 +44,7 @@ struct PsdF64Tables {
     double sc1[12];              // for circ(CIRC)
     double sc2[12];              // for circ(CIRC)^2
     double col8[12];             // 8 * CIRC[(12 - r) % 12]:  8 * C e_0
+    double c_col0[12];           // CIRC[(12 - r) % 12]:  C e_0
     double full_init_s[8][2][12];  // chain-init constants in split form [layer][half][UU(3), UV(3), V(6)]
     double pair_k_s[11][2][12];    // same for the pair constants (lane 0 also carries -8 * pair_t0)
 };
@@ -99,6 +100,7 @@ static inline void psd_f64_build_tables(PsdF64Tables &t) {
             for (int i = 0; i < 12; i++) a += circ[i] * circ[(m - i + 12) % 12];
             c2[m] = (double)a;
             t.col8[m] = 8.0 * (double)circ[(12 - m) % 12];
+            t.c_col0[m] = (double)circ[(12 - m) % 12];
         }
         split_row(c1, t.sc1);
         split_row(c2, t.sc2);
@@ -150,6 +152,9 @@ static inline cudaError_t psd_f64_upload_tables() {
 #define PF_TRACK_FOLD(x)
 #define PF_TRACK_RENORM(x)
 #endif
+#ifndef PF_INT_CVT
+#define PF_INT_CVT 0     // 1: fold / S-box output through 64-bit integer conversions (XU pipe) instead of DADDs (experiment)
+#endif
 #ifndef PF_CVT_MAGIC
 #define PF_CVT_MAGIC 0   // 0: I2F.F64.U32 on the conversion unit; 1: 2^52-mantissa trick (one more DADD, two moves)
 #endif
@@ -182,7 +187,11 @@ GL_HD u64 pf_bits(double x) {
 GL_HD u64 pf_fold(double al, double ah) {
     PF_TRACK_FOLD(al);
     PF_TRACK_FOLD(ah);
+#if defined(__CUDA_ARCH__) && PF_INT_CVT
+    const u64 ua = (u64)(__double2ll_rz(al) + (1ll << 51)), uh = (u64)(__double2ll_rz(ah) + (1ll << 51));
+#else
     const u64 ua = pf_bits(al + PF_MAGIC), uh = pf_bits(ah + PF_MAGIC);   // mantissa = x + 2^51
+#endif
 #ifdef __CUDA_ARCH__
     u32 v0, v1;
     asm("{\n\t"
@@ -233,9 +242,14 @@ GL_HD void pf_pow7(u64 x, double &lo, double &hi) {
     const u64 x4 = gl_sqr(x2);
     const u64 x3 = gl_mul(x, x2);
     const u64 pl = x3 * x4, ph = gl_mulhi64(x3, x4);
+#if defined(__CUDA_ARCH__) && PF_INT_CVT
+    lo = __ll2double_rn((long long)(u64)(u32)pl - (long long)(u64)(u32)ph - (long long)(ph >> 32));
+    hi = __ll2double_rn((long long)((pl >> 32) + (u64)(u32)ph));
+#else
     const double d0 = pf_cvt((u32)pl), d1 = pf_cvt((u32)(pl >> 32)), d2 = pf_cvt((u32)ph), d3 = pf_cvt((u32)(ph >> 32));
     lo = (d0 - d2) - d3;
     hi = d1 + d2;
+#endif
 }
 
 // y = init + circ(c) x as a split convolution (see PsdF64Tables::sc1).  cc = split coefficients, init = split constants.
@@ -340,21 +354,18 @@ GL_HD void pf_partial_rounds(u64 (&s)[12]) {
         double nl[12], nh[12];                          // M^2 W + K: independent of b, overlaps the S-box below
         pf_circ12(al, PF_T(sc2), PF_T(pair_k_s)[p][0], nl);
         pf_circ12(ah, PF_T(sc2), PF_T(pair_k_s)[p][1], nh);
-#pragma unroll
-        for (int r = 0; r < 12; r++) {
-            nl[r] = pf_fma(al[0], PF_T(col8)[r], nl[r]);
-            nh[r] = pf_fma(ah[0], PF_T(col8)[r], nh[r]);
-        }
-        nl[0] = pf_fma(t0l, 8.0, nl[0]);
-        nh[0] = pf_fma(t0h, 8.0, nh[0]);
         double bl, bh;
         pf_pow7(b, bl, bh);
-        const double dl = bl - t0l, dh = bh - t0h;      // (b' - b) + B as a pair
+        // the two rank-1 terms share their direction: W_0 * 8 C e_0 + d * (C e_0 + 8 e_0) = (8 W_0 + d) * C e_0 + 8 d e_0
+        // with d = (b' - b) + B as a pair, and on lane 0  8 T0 + 8 d = 8 b'
+        const double ul = pf_fma(al[0], 8.0, bl - t0l), uh = pf_fma(ah[0], 8.0, bh - t0h);
 #pragma unroll
         for (int r = 0; r < 12; r++) {
-            al[r] = pf_fma(PF_T(m_col0)[r], dl, nl[r]);
-            ah[r] = pf_fma(PF_T(m_col0)[r], dh, nh[r]);
+            al[r] = pf_fma(PF_T(c_col0)[r], ul, nl[r]);
+            ah[r] = pf_fma(PF_T(c_col0)[r], uh, nh[r]);
         }
+        al[0] = pf_fma(bl, 8.0, al[0]);
+        ah[0] = pf_fma(bh, 8.0, ah[0]);
     }
 #pragma unroll
     for (int r = 0; r < 12; r++) s[r] = pf_fold(al[r], ah[r]);
