@@ -95,12 +95,10 @@ GL_HD void plk_poseidon_gate_f64_partial(const W &w, PlkAcc &acc, u64 (&st)[12])
         pf_pow7(in0, al[0], ah[0]);
         double t0l = PF_T(pair_t0)[p][0], t0h = PF_T(pair_t0)[p][1];
 #pragma unroll
-        for (int j = 0; j < 12; j++) {
-            t0l = pf_fma(al[j], PF_T(circ)[j], t0l);
-            t0h = pf_fma(ah[j], PF_T(circ)[j], t0h);
+        for (int j = 0; j < 12; j++) {                  // row 0 of M = circ + 8 e_0 e_0^T
+            t0l = pf_fma(al[j], PF_T(m_row0)[j], t0l);
+            t0h = pf_fma(ah[j], PF_T(m_row0)[j], t0h);
         }
-        t0l = pf_fma(al[0], 8.0, t0l);
-        t0h = pf_fma(ah[0], 8.0, t0h);
         const u64 b = pf_fold(t0l, t0h);
         const u64 in1 = w[65 + 2 * p + 1];
         plk_emit(acc, gl_sub(b, in1));

@@ -17,7 +17,7 @@
 //         b  = (M W + RC_{t+1})[0],   b' = b^7,
 //         state_{t+2} = M^2 W + (M RC_{t+1} + RC_{t+2}) + (b' - b) * M e_0
 //     (M^2 has entries < 2^15, so 2^32 * 264^2 < 2^49 stays exact).  Lanes 1..11 never leave the FP64 domain during
-//     the partial rounds; they are re-normalised to |lo|,|hi| <= 2^31 + 2^19 with 9 FP64 operations every two rounds.
+//     the partial rounds; they are re-normalised to |lo|,|hi| <= 2^31 + 2^19 with 8 FP64 operations every two rounds.
 //     Only lane 0 crosses to the integer side (one fold per round) for its S-box;
 //   * a pair (al, ah) is folded back to a u64 through the mantissa of al + 1.5*2^52 (a bias of 2^51 on both halves,
 //     compensated inside the chain-init constants), then one 10-instruction carry chain.
@@ -231,9 +231,9 @@ GL_HD void pf_renorm(double &lo, double &hi) {
     const double a1 = pf_fma(lo, I32, PF_MAGIC) - PF_MAGIC;   // rint(lo / 2^32)
     const double a0 = pf_fma(a1, N32, lo);
     const double h1 = pf_fma(hi, I32, PF_MAGIC) - PF_MAGIC;
-    const double h0 = pf_fma(h1, N32, hi);
+    const double h01 = pf_fma(h1, -4294967295.0, hi);          // h0 + h1 in one operation (h0 = hi - 2^32 h1)
     lo = a0 - h1;                                              // 2^64 h1 = 2^32 h1 - h1
-    hi = (a1 + h0) + h1;
+    hi = a1 + h01;
 }
 
 // x^7 with the last product left unreduced (x0 + 2^32 x1 + 2^64 x2 + 2^96 x3) and reduced in FP64.
@@ -344,12 +344,10 @@ GL_HD void pf_partial_rounds(u64 (&s)[12]) {
         double t0l = PF_T(pair_t0)[p][0], t0h = PF_T(pair_t0)[p][1];
         // T0 = (C W)[0] + 8 W_0 + const;  M^2 W = circ(c2) W + W_0 * (8 C e_0) + e_0 * 8 (T0 - const)
 #pragma unroll
-        for (int j = 0; j < 12; j++) {
-            t0l = pf_fma(al[j], PF_T(circ)[j], t0l);
-            t0h = pf_fma(ah[j], PF_T(circ)[j], t0h);
+        for (int j = 0; j < 12; j++) {                  // row 0 of M = circ + 8 e_0 e_0^T
+            t0l = pf_fma(al[j], PF_T(m_row0)[j], t0l);
+            t0h = pf_fma(ah[j], PF_T(m_row0)[j], t0h);
         }
-        t0l = pf_fma(al[0], 8.0, t0l);
-        t0h = pf_fma(ah[0], 8.0, t0h);
         const u64 b = pf_fold(t0l, t0h);                // lane 0 entering the second S-box (RC included)
         double nl[12], nh[12];                          // M^2 W + K: independent of b, overlaps the S-box below
         pf_circ12(al, PF_T(sc2), PF_T(pair_k_s)[p][0], nl);
