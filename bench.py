@@ -34,8 +34,8 @@ RATE_BITS = 3
 CAP_HEIGHT = 4
 IMAD_PER_PERM = 6612
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures at configs[1]
-# (profiles/r01_leaves_v1.md, profiles/r01_ntt_v3.md); only quoted when the workload is that configuration
-NCU_TRAFFIC_LEAVES = 9.086e9 + 0.330e9
+# (profiles/r02_leaves_final.md, profiles/r01_ntt_v3.md); only quoted when the workload is that configuration
+NCU_TRAFFIC_LEAVES = 9.086e9 + 0.311e9
 NCU_TRAFFIC_NTT = (1.14 + 1.11 + 1.14 + 1.11 + 1.57 + 9.64 + 9.06 + 9.03) * 1e9
 NOMINAL_IMAD_PER_S = 148 * 64 * 1.965e9   # 64 IMAD/clk/SM; no integer entry in MEASURED_PEAKS.json
 
