@@ -90,8 +90,10 @@ GL_HD void plk_poseidon_gate_f64_partial(const W &w, PlkAcc &acc, u64 (&st)[12])
         const u64 a = pf_fold(al[0], ah[0]);
         const u64 in0 = w[65 + 2 * p];
         plk_emit(acc, gl_sub(a, in0));
+        if (p != 0) {
 #pragma unroll
-        for (int j = 1; j < 12; j++) pf_renorm(al[j], ah[j]);
+            for (int j = 1; j < 12; j++) pf_renorm(al[j], ah[j]);
+        }
         pf_pow7(in0, al[0], ah[0]);
         double t0l = PF_T(pair_t0)[p][0], t0h = PF_T(pair_t0)[p][1];
 #pragma unroll

@@ -153,7 +153,7 @@ static inline cudaError_t psd_f64_upload_tables() {
 #define PF_TRACK_RENORM(x)
 #endif
 #ifndef PF_INT_CVT
-#define PF_INT_CVT 0     // 1: fold / S-box output through 64-bit integer conversions (XU pipe) instead of DADDs (experiment)
+#define PF_INT_CVT 1     // bit 0 = S-box output (faster, default), bit 1 = fold (slower) through 64-bit integer conversions instead of DADDs
 #endif
 #ifndef PF_CVT_MAGIC
 #define PF_CVT_MAGIC 0   // 0: I2F.F64.U32 on the conversion unit; 1: 2^52-mantissa trick (one more DADD, two moves)
@@ -187,7 +187,7 @@ GL_HD u64 pf_bits(double x) {
 GL_HD u64 pf_fold(double al, double ah) {
     PF_TRACK_FOLD(al);
     PF_TRACK_FOLD(ah);
-#if defined(__CUDA_ARCH__) && PF_INT_CVT
+#if defined(__CUDA_ARCH__) && (PF_INT_CVT & 2)
     const u64 ua = (u64)(__double2ll_rz(al) + (1ll << 51)), uh = (u64)(__double2ll_rz(ah) + (1ll << 51));
 #else
     const u64 ua = pf_bits(al + PF_MAGIC), uh = pf_bits(ah + PF_MAGIC);   // mantissa = x + 2^51
@@ -242,9 +242,11 @@ GL_HD void pf_pow7(u64 x, double &lo, double &hi) {
     const u64 x4 = gl_sqr(x2);
     const u64 x3 = gl_mul(x, x2);
     const u64 pl = x3 * x4, ph = gl_mulhi64(x3, x4);
-#if defined(__CUDA_ARCH__) && PF_INT_CVT
-    lo = __ll2double_rn((long long)(u64)(u32)pl - (long long)(u64)(u32)ph - (long long)(ph >> 32));
-    hi = __ll2double_rn((long long)((pl >> 32) + (u64)(u32)ph));
+#if (PF_INT_CVT & 1)
+    // the two limb sums as 64-bit integers (|lo| < 2^34, hi < 2^33), one exact conversion each: 2 I2F.F64.S64 + 4 integer
+    // instructions instead of 4 I2F.F64.U32 + 3 DADD (0.9 % faster on sm_100a: the FP64 pipe is the busier one)
+    lo = (double)((long long)(u64)(u32)pl - (long long)(u64)(u32)ph - (long long)(ph >> 32));
+    hi = (double)(long long)((pl >> 32) + (u64)(u32)ph);
 #else
     const double d0 = pf_cvt((u32)pl), d1 = pf_cvt((u32)(pl >> 32)), d2 = pf_cvt((u32)ph), d3 = pf_cvt((u32)(ph >> 32));
     lo = (d0 - d2) - d3;
@@ -338,8 +340,10 @@ GL_HD void pf_partial_rounds(u64 (&s)[12]) {
     PF_UNROLL1
     for (int p = 0; p < 11; p++) {
         const u64 a = pf_fold(al[0], ah[0]);
+        if (p != 0) {                                   // step 0 starts from fresh 32-bit limbs
 #pragma unroll
-        for (int j = 1; j < 12; j++) pf_renorm(al[j], ah[j]);
+            for (int j = 1; j < 12; j++) pf_renorm(al[j], ah[j]);
+        }
         pf_pow7(a, al[0], ah[0]);                       // W
         double t0l = PF_T(pair_t0)[p][0], t0h = PF_T(pair_t0)[p][1];
         // T0 = (C W)[0] + 8 W_0 + const;  M^2 W = circ(c2) W + W_0 * (8 C e_0) + e_0 * 8 (T0 - const)
