@@ -68,18 +68,51 @@ static inline u64 orc_sbox7r(u64 x) {
 }
 static inline u64 orc_addc(u64 s, u64 c) {         /* s any u64, c canonical: one wrap at most */
     u64 t = s + c;
-    return t + ((t < s) ? GL_EPS : 0);
+    return t + (GL_EPS & (0 - (u64)(t < s)));      /* branch-free: the carry is a coin flip */
+}
+/* y = 4 * circ(CIRC) x, out[r] = sum_i x[(i+r)%12] * CIRC[i], as a split correlation: 12 -> cyclic 6 + negacyclic 6, the cyclic
+ * half again 3 + 3: 54 products instead of 144.  plonky2 does the same job on x86-64 with its FFT-based `mds_multiply_freq`
+ * on the 32-bit halves [DEP plonky2:hash/poseidon_goldilocks.rs]; this is the equivalent, cheaper MDS of the production
+ * form.  orc_mds above stays the direct 144-product form of the independent (naive) permutation. */
+static inline void orc_circ12_x4(const long long x[12], long long y[12]) {
+    static const long long CPP[3] = {
+        (long long)(ORC_MDS_CIRC[0] + ORC_MDS_CIRC[3] + ORC_MDS_CIRC[6] + ORC_MDS_CIRC[9]),
+        (long long)(ORC_MDS_CIRC[1] + ORC_MDS_CIRC[4] + ORC_MDS_CIRC[7] + ORC_MDS_CIRC[10]),
+        (long long)(ORC_MDS_CIRC[2] + ORC_MDS_CIRC[5] + ORC_MDS_CIRC[8] + ORC_MDS_CIRC[11])};
+    static const long long CPQ[3] = {
+        (long long)ORC_MDS_CIRC[0] - (long long)ORC_MDS_CIRC[3] + (long long)ORC_MDS_CIRC[6] - (long long)ORC_MDS_CIRC[9],
+        (long long)ORC_MDS_CIRC[1] - (long long)ORC_MDS_CIRC[4] + (long long)ORC_MDS_CIRC[7] - (long long)ORC_MDS_CIRC[10],
+        (long long)ORC_MDS_CIRC[2] - (long long)ORC_MDS_CIRC[5] + (long long)ORC_MDS_CIRC[8] - (long long)ORC_MDS_CIRC[11]};
+    static const long long CQ[6] = {
+        (long long)ORC_MDS_CIRC[0] - (long long)ORC_MDS_CIRC[6], (long long)ORC_MDS_CIRC[1] - (long long)ORC_MDS_CIRC[7],
+        (long long)ORC_MDS_CIRC[2] - (long long)ORC_MDS_CIRC[8], (long long)ORC_MDS_CIRC[3] - (long long)ORC_MDS_CIRC[9],
+        (long long)ORC_MDS_CIRC[4] - (long long)ORC_MDS_CIRC[10], (long long)ORC_MDS_CIRC[5] - (long long)ORC_MDS_CIRC[11]};
+    long long P[6], Q[6], PP[3], PQ[3], U[6];
+    for (int j = 0; j < 6; j++) { P[j] = x[j] + x[j + 6]; Q[j] = x[j] - x[j + 6]; }
+    for (int j = 0; j < 3; j++) { PP[j] = P[j] + P[j + 3]; PQ[j] = P[j] - P[j + 3]; }
+    for (int r = 0; r < 3; r++) {
+        long long uu = 0, uv = 0;
+        for (int i = 0; i < 3; i++) uu += PP[(i + r) % 3] * CPP[i];
+        for (int i = 0; i < 3; i++) uv += (i + r >= 3 ? -PQ[(i + r) % 3] : PQ[(i + r) % 3]) * CPQ[i];
+        U[r] = uu + uv;
+        U[r + 3] = uu - uv;
+    }
+    for (int r = 0; r < 6; r++) {
+        long long v = 0;
+        for (int i = 0; i < 6; i++) v += (i + r >= 6 ? -Q[(i + r) % 6] : Q[(i + r) % 6]) * CQ[i];
+        y[r] = U[r] + 2 * v;
+        y[r + 6] = U[r] - 2 * v;
+    }
 }
 static inline void orc_mds_r(u64 s[12]) {
-    u64 lo[24], hi[24], o[12];
-    for (int i = 0; i < 12; i++) { lo[i] = lo[i + 12] = s[i] & GL_EPS; hi[i] = hi[i + 12] = s[i] >> 32; }
-    for (int r = 0; r < 12; r++) {
-        u64 al = 0, ah = 0;
-        for (int i = 0; i < 12; i++) { al += lo[i + r] * ORC_MDS_CIRC[i]; ah += hi[i + r] * ORC_MDS_CIRC[i]; }
-        if (r == 0) { al += lo[0] * POSEIDON_MDS_DIAG0; ah += hi[0] * POSEIDON_MDS_DIAG0; }
-        o[r] = orc_red128((u128)al + ((u128)ah << 32));
-    }
-    for (int r = 0; r < 12; r++) s[r] = o[r];
+    /* on 32-bit halves: every true sum is in [0, 2^42), the x4 intermediates below 2^45 in magnitude */
+    long long lo[12], hi[12], yl[12], yh[12];
+    for (int i = 0; i < 12; i++) { lo[i] = (long long)(s[i] & GL_EPS); hi[i] = (long long)(s[i] >> 32); }
+    orc_circ12_x4(lo, yl);
+    orc_circ12_x4(hi, yh);
+    yl[0] += 4 * (long long)POSEIDON_MDS_DIAG0 * lo[0];
+    yh[0] += 4 * (long long)POSEIDON_MDS_DIAG0 * hi[0];
+    for (int r = 0; r < 12; r++) s[r] = orc_red128((u128)(u64)(yl[r] >> 2) + ((u128)(u64)(yh[r] >> 2) << 32));
 }
 /* sum of up to 12 products of u64s, accumulated as (low words, high words): no carry tracking, 2^64 = eps at the end
  * (what plonky2's reduce_u160 / mds_partial_layer_fast achieve with a u160 accumulator) */
