@@ -9,14 +9,17 @@
 // 64x64 products with 64-bit constants per round: 852 alu/fma issue cycles per round per warp).  B200 keeps a
 // 64-lane/clk/SM FP64 pipe that such a kernel leaves idle.  Here
 //   * a lane is carried as a pair of doubles (lo, hi) meaning lo + 2^32*hi (mod p), both signed integers < 2^51;
-//   * the S-box runs on the integer pipes (3 reduced products + 1 unreduced 128-bit product x0..x3), and the final
-//     reduction 2^64 = 2^32 - 1, 2^96 = -1 happens in FP64:  lo = x0 - x2 - x3,  hi = x1 + x2;
-//   * the MDS layer (coefficients <= 41) is 2 x 145 DFMA per layer; the NEXT round's constants are the initial
-//     values of the accumulation chains, so adding round constants costs nothing;
+//   * the S-box runs on the integer pipes (3 reduced products + 1 unreduced 128-bit product x0..x3); the final
+//     reduction 2^64 = 2^32 - 1, 2^96 = -1 is left to the pair:  lo = x0 - x2 - x3,  hi = x1 + x2  (two small integer
+//     sums, one exact conversion each);
+//   * the MDS layer (coefficients <= 41) is a 12-point circular correlation computed as a split convolution (pf_circ12:
+//     90 FP64 operations per half instead of 144); the NEXT round's constants are the initial values of the accumulation
+//     chains, so adding round constants costs nothing;
 //   * the 22 partial rounds run in their NAIVE form, two rounds per step: with W = state after the first S-box,
-//         b  = (M W + RC_{t+1})[0],   b' = b^7,
-//         state_{t+2} = M^2 W + (M RC_{t+1} + RC_{t+2}) + (b' - b) * M e_0
-//     (M^2 has entries < 2^15, so 2^32 * 264^2 < 2^49 stays exact).  Lanes 1..11 never leave the FP64 domain during
+//         b  = (M W + RC_{t+1})[0],   b' = b^7,   d = b' - b,
+//         state_{t+2} = M^2 W + (M RC_{t+1} + RC_{t+2}) + d * M e_0
+//                     = C^2 W + K + (8 W_0 + d) * C e_0 + 8 b' e_0          (M = C + 8 e_0 e_0^T, C = circ)
+//     (C^2 has entries < 2^15, so 2^32 * 264^2 < 2^49 stays exact).  Lanes 1..11 never leave the FP64 domain during
 //     the partial rounds; they are re-normalised to |lo|,|hi| <= 2^31 + 2^19 with 8 FP64 operations every two rounds.
 //     Only lane 0 crosses to the integer side (one fold per round) for its S-box;
 //   * a pair (al, ah) is folded back to a u64 through the mantissa of al + 1.5*2^52 (a bias of 2^51 on both halves,
@@ -35,15 +38,12 @@ struct PsdF64Tables {
     double full_init[8][12][2];  // chain-init constants of the 8 full-round MDS layers [layer][lane][lo, hi]
     double pair_t0[11][2];       // RC_{t+1}[0] - B
     double pair_k[11][12][2];    // M RC_{t+1} + RC_{t+2} - B * M e_0 (- B where the lane is folded next)
-    double m2[12][12];           // M^2
     double m_row0[12];           // M[0][j]
-    double m_col0[12];           // M[r][0]
     double circ[12];             // MDS_MATRIX_CIRC
     // split-convolution form (PF_SPLIT): a 12-point circular correlation as (6 cyclic + 6 negacyclic), the cyclic half
     // again as (3 + 3): 90 FP64 operations instead of 144.  [0..3) = cPP, [3..6) = cPQ, [6..12) = cQ
     double sc1[12];              // for circ(CIRC)
     double sc2[12];              // for circ(CIRC)^2
-    double col8[12];             // 8 * CIRC[(12 - r) % 12]:  8 * C e_0
     double c_col0[12];           // CIRC[(12 - r) % 12]:  C e_0
     double full_init_s[8][2][12];  // chain-init constants in split form [layer][half][UU(3), UV(3), V(6)]
     double pair_k_s[11][2][12];    // same for the pair constants (lane 0 also carries -8 * pair_t0)
@@ -70,15 +70,8 @@ static inline void psd_f64_build_tables(PsdF64Tables &t) {
     for (int r = 0; r < 12; r++)
         for (int i = 0; i < 12; i++) M[r][(i + r) % 12] += circ[i];
     M[0][0] += POSEIDON_MDS_DIAG0;
-    for (int r = 0; r < 12; r++)
-        for (int j = 0; j < 12; j++) {
-            u64 a = 0;
-            for (int k = 0; k < 12; k++) a += M[r][k] * M[k][j];
-            t.m2[r][j] = (double)a;
-        }
     for (int j = 0; j < 12; j++) {
         t.m_row0[j] = (double)M[0][j];
-        t.m_col0[j] = (double)M[j][0];
         t.circ[j] = (double)circ[j];
     }
     auto sub = [](u64 a, u64 b) { return a >= b ? a - b : a + (GL_P - b); };   // canonical a, b
@@ -99,7 +92,6 @@ static inline void psd_f64_build_tables(PsdF64Tables &t) {
             u64 a = 0;
             for (int i = 0; i < 12; i++) a += circ[i] * circ[(m - i + 12) % 12];
             c2[m] = (double)a;
-            t.col8[m] = 8.0 * (double)circ[(12 - m) % 12];
             t.c_col0[m] = (double)circ[(12 - m) % 12];
         }
         split_row(c1, t.sc1);
