@@ -35,19 +35,52 @@
 // ---- the alpha-weighted running sum of constraints for both challenges ----
 // alpha^t comes from a table built on the host (every thread walks the same constraint sequence, so the loads are
 // warp-uniform): one multiply-add per term and challenge.
+// sum_t alpha^t term_t per challenge, LAZY: a 160-bit accumulator of unreduced 128-bit products (acc160, poseidon.cuh),
+// reduced once per gate -- an emit is a product and a carry chain instead of a product and a reduction (2 of every 5
+// field products of a gate-heavy circuit are these accumulations).
 struct PlkAcc {
-    u64 sum[PLK_MAX_CHALLENGES];   // sum_t alpha^t term_t
-    const u64 *apow;               // [PLK_MAX_CHALLENGES][stride] powers of alpha
+    acc160 s[PLK_MAX_CHALLENGES];
+    const u64 *apow;               // [PLK_MAX_CHALLENGES][stride] powers of alpha (canonical)
     u32 stride;
     u32 t;                         // index of the next term
 };
+GL_HD void plk_acc_init(PlkAcc &a, const u64 *apow, u32 stride, u32 t0) {
+#pragma unroll
+    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.s[c].lo = a.s[c].hi = 0, a.s[c].top = 0;
+    a.apow = apow; a.stride = stride; a.t = t0;
+}
+GL_HD u64 plk_acc_value(const PlkAcc &a, int c) { return acc160_reduce(a.s[c]); }
 GL_HD void plk_emit(PlkAcc &a, u64 term) {
 #pragma unroll
-    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.sum[c] = gl_mul_add(a.apow[c * a.stride + a.t], term, a.sum[c]);
+    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) acc160_mac(a.s[c], a.apow[c * a.stride + a.t], term);
     a.t++;
 }
 // the same for a term whose index is not the running one
 GL_HD void plk_emit_at(PlkAcc &a, u32 t, u64 term) {
+#pragma unroll
+    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) acc160_mac(a.s[c], a.apow[c * a.stride + t], term);
+}
+// The same interface with the sum reduced at every emit: 2 registers per challenge instead of 5.  For the evaluators
+// that are short of registers and emit little (native PoseidonGate: 106 instead of 96 registers and spills with the lazy
+// form; permutation checks: 22 terms).
+struct PlkAccR {
+    u64 sum[PLK_MAX_CHALLENGES];
+    const u64 *apow;
+    u32 stride;
+    u32 t;
+};
+GL_HD void plk_acc_init(PlkAccR &a, const u64 *apow, u32 stride, u32 t0) {
+#pragma unroll
+    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.sum[c] = 0;
+    a.apow = apow; a.stride = stride; a.t = t0;
+}
+GL_HD u64 plk_acc_value(const PlkAccR &a, int c) { return a.sum[c]; }
+GL_HD void plk_emit(PlkAccR &a, u64 term) {
+#pragma unroll
+    for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.sum[c] = gl_mul_add(a.apow[c * a.stride + a.t], term, a.sum[c]);
+    a.t++;
+}
+GL_HD void plk_emit_at(PlkAccR &a, u32 t, u64 term) {
 #pragma unroll
     for (int c = 0; c < PLK_MAX_CHALLENGES; c++) a.sum[c] = gl_mul_add(a.apow[c * a.stride + t], term, a.sum[c]);
 }
@@ -75,8 +108,8 @@ struct PlkCols {
 #define PLK_F64_LANES 3   // S-box lanes per rolled iteration (code size: the kernel must stay inside the instruction cache)
 #endif
 // the 22 partial rounds of the gate, two per step: pf_partial_rounds with both S-box inputs constrained and replaced
-template <class W>
-GL_HD void plk_poseidon_gate_f64_partial(const W &w, PlkAcc &acc, u64 (&st)[12]) {
+template <class W, class A>
+GL_HD void plk_poseidon_gate_f64_partial(const W &w, A &acc, u64 (&st)[12]) {
     double al[12], ah[12];
 #pragma unroll
     for (int j = 0; j < 12; j++) {
@@ -122,8 +155,8 @@ GL_HD void plk_poseidon_gate_f64_partial(const W &w, PlkAcc &acc, u64 (&st)[12])
 #pragma unroll
     for (int i = 0; i < 12; i++) st[i] = pf_fold(al[i], ah[i]);          // state + RC_26
 }
-template <class W>
-GL_HD void plk_poseidon_gate_f64(const W &w, PlkAcc &acc) {
+template <class W, class A>
+GL_HD void plk_poseidon_gate_f64(const W &w, A &acc) {
     const u64 swap = w[24];
     plk_emit(acc, gl_mul(swap, gl_sub(swap, 1)));
     u64 st[12];
@@ -267,9 +300,8 @@ GL_HD void quot_perm_point(const QuotParams &p, u64 t) {
     const u32 nc = p.num_selectors + p.num_gate_constants, nch = p.num_challenges, npp = p.npp;
     // i + Lq / n keeps the low bits of i, i.e. the high bits of pos: pos_next lies in the same row shard (<= 2^qdb shards)
     PlkCols sig = {p.cs + (u64)nc * p.stride, p.stride, t}, w = {p.wires, p.stride, t}, zs = {p.zs, p.stride, t}, zn = {p.zs, p.stride, pos_next - p.pos0};
-    PlkAcc acc;
-    for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
-    acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = 0;
+    PlkAccR acc;
+    plk_acc_init(acc, p.apow, p.apow_stride, 0);
     const u64 l0 = p.l0[pos];
     for (u32 c = 0; c < nch; c++) plk_emit(acc, gl_mul(l0, gl_sub(zs[c], 1)));
     // partial-product checks.  plonky2 orders the terms challenge-major (term index nch + c (npp + 1) + t); the loops run
@@ -300,7 +332,7 @@ GL_HD void quot_perm_point(const QuotParams &p, u64 t) {
             }
         }
     }
-    for (u32 c = 0; c < nch; c++) p.acc[(u64)c * p.count + t] = acc.sum[c];
+    for (u32 c = 0; c < nch; c++) p.acc[(u64)c * p.count + t] = plk_acc_value(acc, c);
 }
 
 // PoseidonGate, native: acc += filter * sum_t alpha^(first_gate_term + t) c_t
@@ -308,13 +340,12 @@ GL_HD void quot_poseidon_point(const QuotParams &p, u64 t) {
     PlkCols cs = {p.cs, p.stride, t}, w = {p.wires, p.stride, t};
     const PlkGateDev &g = p.poseidon;
     const u64 filter = plk_filter(g.row, g.group_start, g.group_end, cs[g.selector_index], p.num_selectors > 1);
-    PlkAcc acc;
-    for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
-    acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = p.first_gate_term;
+    PlkAccR acc;
+    plk_acc_init(acc, p.apow, p.apow_stride, p.first_gate_term);
     plk_poseidon_gate_f64(w, acc);
     for (u32 c = 0; c < p.num_challenges; c++) {
         u64 *a = &p.acc[(u64)c * p.count + t];
-        *a = gl_mul_add(filter, acc.sum[c], *a);
+        *a = gl_mul_add(filter, plk_acc_value(acc, c), *a);
     }
 }
 
@@ -341,12 +372,11 @@ GL_HD void quot_gates_point(const QuotParams &p, u64 t) {
         if (g.prog_len == 0 || (g.native == 1 && p.has_poseidon) || (g.native == 2 && p.use_native_gates)) continue;
         const u64 filter = plk_filter(g.row, g.group_start, g.group_end, cs[g.selector_index], p.num_selectors > 1);
         PlkAcc acc;
-        for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
-        acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = p.first_gate_term;
+        plk_acc_init(acc, p.apow, p.apow_stride, p.first_gate_term);
         QuotGvmEmit em = {&acc};
         gvm_run<GvmBaseField>(p.prog + g.prog_off, g.prog_len, cx, regs, em);
 #pragma unroll
-        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) total[c] = gl_mul_add(filter, acc.sum[c], total[c]);
+        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) total[c] = gl_mul_add(filter, plk_acc_value(acc, c), total[c]);
     }
     for (u32 c = 0; c < p.num_challenges; c++) {
         u64 *a = &p.acc[(u64)c * p.count + t];
@@ -404,8 +434,7 @@ GL_HD void quot_native_point(const QuotParams &p, u64 t) {
         if (g.native != 2 || !p.use_native_gates || !((kind_mask >> g.kind) & 1)) continue;
         const u64 filter = plk_filter(g.row, g.group_start, g.group_end, cs[g.selector_index], p.num_selectors > 1);
         PlkAcc acc;
-        for (u32 c = 0; c < PLK_MAX_CHALLENGES; c++) acc.sum[c] = 0;
-        acc.apow = p.apow; acc.stride = p.apow_stride; acc.t = p.first_gate_term;
+        plk_acc_init(acc, p.apow, p.apow_stride, p.first_gate_term);
         QuotDirect ev = {{p.wires, p.stride, t}, {p.cs + (u64)p.num_selectors * p.stride, p.stride, t}, p.imm, &acc};
 #define PLK_NATIVE_CASE(K) if constexpr ((KIND_MASK >> (K)) & 1) { if (g.kind == (K)) plk_build_gate(ev, (u32)(K), g.p, p.num_wires, p.num_routed, p.num_gate_constants); }
         PLK_NATIVE_CASE(PLK_CONSTANT) PLK_NATIVE_CASE(PLK_PUBLIC_INPUT) PLK_NATIVE_CASE(PLK_ARITHMETIC) PLK_NATIVE_CASE(PLK_BASE_SUM)
@@ -416,7 +445,7 @@ GL_HD void quot_native_point(const QuotParams &p, u64 t) {
         PLK_NATIVE_CASE(PLK_U32_INTERLEAVE) PLK_NATIVE_CASE(PLK_UNINTERLEAVE_TO_U32) PLK_NATIVE_CASE(PLK_UNINTERLEAVE_TO_B32)
 #undef PLK_NATIVE_CASE
 #pragma unroll
-        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) total[c] = gl_mul_add(filter, acc.sum[c], total[c]);
+        for (int c = 0; c < PLK_MAX_CHALLENGES; c++) total[c] = gl_mul_add(filter, plk_acc_value(acc, c), total[c]);
     }
     for (u32 c = 0; c < p.num_challenges; c++) {
         u64 *a = &p.acc[(u64)c * p.count + t];
