@@ -64,3 +64,22 @@ def test_rust_sys_declarations_match_the_header():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"])
     assert r.returncode == 0, "run python tools/gen_rust_sys.py"
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's keys,
+    the sample it really ran and a zero-copy e2e object.  Tiny workload here; no GPU involved."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--log-n", "10"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "commit_throughput" and line["unit"] == "GB/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 1
+    assert line["config"]["sample_log_rows"] <= 10 and "workload" in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
